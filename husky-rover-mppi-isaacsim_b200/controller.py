@@ -1,0 +1,352 @@
+"""Host-side mirror of the reference controller interface (drop-in boundary).
+
+Mirrors thesis_master/warp_implementation/MPPI_isaac.py: `Surface` (:259-378), `Robot` (:381-400) and
+`MPPI_Controller` (:402-805) keep their constructor signatures, method names (`warp_setup`, `reset`,
+`MPPI_step`, `run`) and the attributes the Isaac driver reads and writes between steps
+(visual_terrain_stack_full_terrain.py:466-576).  Where the reference issues nine Warp launches per
+iteration, `MPPI_step` makes ONE call into libmppi_b200.so.  There is no CPU fallback: without the
+CUDA library and a GPU the step raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import yaml
+
+from . import capi
+from .devarray import DeviceArray, to_device_f32, view_device_memory
+
+
+# --------------------------------------------------------------------------------------------- Surface
+class Surface:
+    """DEM + obstacle costmap container, MPPI_isaac.py:259-378 (same constructor signature)."""
+
+    def __init__(self, which_map, filename, which_costmap, costmap_file, grid_size, half_width, origin, bumps,
+                 radius_robot, obstacles=[]):
+        self.grid_size = grid_size
+        self.r_robot = radius_robot
+        self.half_width = half_width
+        self.resolution = 2 * self.half_width / self.grid_size                 # MPPI_isaac.py:265
+        self.costmap_size = int(self.grid_size / 8)                            # MPPI_isaac.py:271
+        self.costmap_resolution = 2 * self.half_width / self.costmap_size      # MPPI_isaac.py:272
+        self.Z = np.zeros((grid_size, grid_size), dtype=np.float32)
+        self.costmap = np.zeros((self.costmap_size, self.costmap_size), dtype=np.float32)
+        self.obstacles = obstacles
+        if which_map == "manual":
+            self.Z = self.create_surface(bumps)
+        elif which_map == "imported":
+            self.Z = np.load(filename)
+        if which_costmap == "manual":
+            self.costmap = self.create_obstacles_costmap(obstacles, origin)
+        if which_map == "imported" and costmap_file:
+            self.costmap = np.load(costmap_file)
+
+    def create_surface(self, bumps) -> np.ndarray:
+        """Crater field: sum of (h-0.5) exp(-r^2/2w^2) - (h+0.5) exp(-r^2/2(w/2)^2), MPPI_isaac.py:317-320."""
+        x = np.linspace(-self.half_width, self.half_width, self.grid_size)
+        X, Y = np.meshgrid(x, x)
+        Z = np.zeros_like(X)
+        for (cx, cy), h, w in bumps:
+            r2 = (X - cx) ** 2 + (Y - cy) ** 2
+            Z += (h - 0.5) * np.exp(-r2 / (2 * w ** 2))
+            Z -= (h + 0.5) * np.exp(-r2 / (2 * (w / 2) ** 2))
+        return Z
+
+    def create_obstacles_costmap(self, obstacles, origin, power: float = 20.0) -> np.ndarray:
+        """Disc rasterisation + L2 distance transform + (1-d)^20, MPPI_isaac.py:361-378."""
+        import cv2
+        n = self.costmap_size
+        xc = np.linspace(-self.half_width, self.half_width, n)
+        Xc, Yc = np.meshgrid(xc, xc)
+        free = 255 * np.ones((n, n), dtype=np.uint8)
+        x0, y0 = origin
+        for x_global, y_global, r_obs in obstacles:
+            x_local = y_global - y0
+            y_local = x_global - x0
+            total_radius = r_obs / 2 + self.r_robot + 0.1
+            free[(Xc - x_local) ** 2 + (Yc - y_local) ** 2 <= total_radius ** 2] = 0
+        dist = cv2.distanceTransform(free, cv2.DIST_L2, 5)
+        dist = cv2.normalize(dist, None, 0, 1.0, cv2.NORM_MINMAX)
+        return (1 - dist) ** power
+
+
+# --------------------------------------------------------------------------------------------- Robot
+class Robot:
+    """Pose history + wheel speeds, MPPI_isaac.py:381-400."""
+
+    def __init__(self, x, y, heading_vector, config_file):
+        with open(config_file, "r") as f:
+            config = yaml.safe_load(f)
+        self.x = [x]
+        self.y = [y]
+        self.z = [0]
+        self.lin_vel = []
+        self.ang_vel = []
+        self.heading_vector = np.array(heading_vector, dtype=np.float64) / np.linalg.norm(heading_vector)
+        self.radius = config["frame_work"]["robot_radius"]
+        self.left_wheel_speed = 0.0
+        self.right_wheel_speed = 0.0
+
+    def update_position(self, new_x, new_y, new_z, new_heading):
+        self.x.append(new_x)
+        self.y.append(new_y)
+        self.z.append(new_z)
+        self.heading_vector = new_heading
+
+
+# --------------------------------------------------------------------------------------------- Controller
+class MPPI_Controller:
+    """Drop-in for MPPI_isaac.MPPI_Controller backed by the fused sm_100a kernel.
+
+    Extra keyword arguments (all optional, defaults reproduce the reference behaviour):
+      math    "strict" (bit-reproducible vs the oracle) | "fast"
+      device  CUDA device index
+      seed    Philox seed (the reference seeds its host generator with 42, MPPI_isaac.py:409)
+    """
+
+    def __init__(self, surface, robot, config_path, goal_x, goal_y, goal_orientation, *, math: str = "strict",
+                 device: int = 0, seed: int = 42, overrides: Optional[dict] = None):
+        with open(config_path, "r") as f:
+            config = yaml.safe_load(f)
+        self.rng = np.random.default_rng(seed=42)
+        self.robot = robot
+        self.surface = surface
+        self.goal_x = goal_x
+        self.goal_y = goal_y
+        self.goal = (goal_x, goal_y)
+        self.goal_orientation = goal_orientation
+        self.loop = 0
+
+        c = config["controller"]
+        self.number_of_iterations = int(c["number_of_iterations"])
+        self.dt = float(c["dt"])
+        self.number_of_trajectories = int(c["number_of_trajectories"])
+        v, i = config["velocities"], config["inputs"]
+        self.initial_linear_velocity = float(v["initial_linear_velocity"])
+        self.initial_angular_velocity = float(v["initial_angular_velocity"])
+        self.v_min_linear, self.v_max_linear = float(v["min_linear_velocity"]), float(v["max_linear_velocity"])
+        self.v_min_angular, self.v_max_angular = float(v["min_angular_velocity"]), float(v["max_angular_velocity"])
+        self.std_dev_u1, self.std_dev_u2 = float(i["std_dev_u1"]), float(i["std_dev_u2"])
+        self.min_u1, self.max_u1 = float(i["min_u1"]), float(i["max_u1"])
+        self.min_u2, self.max_u2 = float(i["min_u2"]), float(i["max_u2"])
+        self.temperature = float(config["cost_evaluation"]["temperature"])
+        if overrides:
+            for k, val in overrides.items():
+                setattr(self, k, val)
+        self.horizon = self.dt * self.v_max_linear * self.number_of_iterations     # MPPI_isaac.py:440
+
+        self.math = {"strict": capi.MATH_STRICT, "fast": capi.MATH_FAST}[math]
+        self.device = torch.device("cuda", device)
+        self.seed = int(seed)
+        self._handle = None
+        self._step_count = 0
+        self._sim_stale = True
+        self._last_state = None
+        self._last_proj = capi.PROJ_3D
+        self._last_offset = 0
+        self._injected_noise = None
+
+    # ------------------------------------------------------------------ setup
+    def _params(self) -> capi.MppiParams:
+        p = capi.default_params(self.number_of_trajectories, self.number_of_iterations)
+        p.math = self.math
+        p.dt = self.dt
+        p.u1_min, p.u1_max, p.u2_min, p.u2_max = self.min_u1, self.max_u1, self.min_u2, self.max_u2
+        p.v_min, p.v_max = self.v_min_linear, self.v_max_linear
+        p.w_min, p.w_max = self.v_min_angular, self.v_max_angular
+        p.lam = self.temperature
+        p.r_wheels = float(self.robot.radius)
+        p.horizon = self.horizon
+        p.target_speed = self.v_max_linear
+        return p
+
+    def warp_setup(self):
+        """Allocates device state and uploads the terrain (replaces MPPI_isaac.py:442-487).  The name is kept
+        for drop-in compatibility; nothing here uses Warp."""
+        if not torch.cuda.is_available():
+            raise capi.MppiError("MPPI_Controller needs a CUDA device (no CPU fallback)")
+        L = capi.lib()
+        self._lib = L
+        if self._handle is not None:
+            L.mppi_destroy(self._handle)
+        h = C.c_void_p()
+        self._p = self._params()
+        capi.check(L.mppi_create(C.byref(self._p), self.device.index, 1, C.byref(h)), "mppi_create")
+        self._handle = h
+        T, K = self.number_of_iterations, self.number_of_trajectories
+        out = capi.MppiOutputs()
+        capi.check(L.mppi_get_outputs(h, C.byref(out)), "mppi_get_outputs")
+        dev = self.device
+        self.optimal_u1_wp = DeviceArray(view_device_memory(out.optimal_u1, (T,), dev))
+        self.optimal_u2_wp = DeviceArray(view_device_memory(out.optimal_u2, (T,), dev))
+        self.optimal_lin_vel_wp = DeviceArray(view_device_memory(out.optimal_v, (T,), dev))
+        self.optimal_ang_vel_wp = DeviceArray(view_device_memory(out.optimal_w, (T,), dev))
+        self.optimal_lin_vel_wp.tensor.fill_(self.initial_linear_velocity)       # MPPI_isaac.py:453-454
+        self.optimal_ang_vel_wp.tensor.fill_(self.initial_angular_velocity)
+        self.costs_wp = DeviceArray(view_device_memory(out.costs, (K,), dev))
+        self._stats = view_device_memory(out.stats, (capi.STATS_STRIDE,), dev)
+        self.trajectories_sim = DeviceArray(view_device_memory(out.sim_traj, (T, 3), dev), on_read=self._ensure_sim)
+        self.heading_vectors_sim = DeviceArray(view_device_memory(out.sim_heading, (T, 3), dev),
+                                               on_read=self._ensure_sim)
+        self._Z = to_device_f32(self.surface.Z, dev)
+        self.costmap_wp = DeviceArray(to_device_f32(self.surface.costmap, dev))
+        self._terrain_dirty = True
+        self._cmd = (C.c_float * 2)()
+        self._stream = torch.cuda.current_stream(dev).cuda_stream
+        torch.cuda.synchronize(dev)
+
+    setup = warp_setup
+
+    # Z_wp can be re-pointed at another device array between steps (driver :567): zero-copy.
+    @property
+    def Z_wp(self):
+        return DeviceArray(self._Z)
+
+    @Z_wp.setter
+    def Z_wp(self, arr):
+        self._Z = to_device_f32(arr, self.device)
+        self._terrain_dirty = True
+
+    def _push_terrain(self):
+        s = self.surface
+        gs, cms = int(s.grid_size), int(s.costmap_size)
+        if self._Z.numel() != gs * gs or self.costmap_wp.tensor.numel() != cms * cms:
+            raise capi.MppiError("terrain arrays do not match surface.grid_size / costmap_size")
+        t = capi.MppiTerrain(self._Z.data_ptr(), gs, float(s.half_width), float(s.resolution),
+                             self.costmap_wp.tensor.data_ptr(), cms, float(s.costmap_resolution))
+        capi.check(self._lib.mppi_set_terrain(self._handle, C.byref(t)), "mppi_set_terrain")
+        self._terrain_dirty = False
+
+    # ------------------------------------------------------------------ per-step
+    def reset(self, controller_or_sim):
+        """The reference rebuilds per-sample scratch here (MPPI_isaac.py:489-503); the fused kernel keeps all
+        per-sample state in registers, so there is nothing to reset."""
+        return None
+
+    def _state(self) -> capi.MppiState:
+        r = self.robot
+        hv = np.asarray(r.heading_vector, dtype=np.float64)
+        hv = hv / np.linalg.norm(hv)                                     # MPPI_isaac.py:493
+        return capi.MppiState(float(r.x[-1]), float(r.y[-1]), float(hv[0]), float(hv[1]), float(hv[2]),
+                              float(r.left_wheel_speed), float(r.right_wheel_speed),
+                              float(self.std_dev_u1), float(self.std_dev_u2),
+                              float(self.goal_x), float(self.goal_y), float(self.goal_orientation))
+
+    def inject_noise(self, eps: Optional[torch.Tensor]):
+        """Validation mode: eps is a device float32 tensor [2, K, T] of standard-normal noise used by the next
+        steps instead of the Philox stream (None restores production mode)."""
+        if eps is not None:
+            K, T = self.number_of_trajectories, self.number_of_iterations
+            if tuple(eps.shape) != (2, K, T) or eps.dtype != torch.float32 or not eps.is_cuda:
+                raise ValueError("eps must be a float32 CUDA tensor of shape [2, K, T]")
+            eps = eps.contiguous()
+        self._injected_noise = eps
+
+    def MPPI_step(self, proj="3d"):
+        """One MPPI iteration (replaces MPPI_isaac.py:505-720).  Asynchronous; results stay on the device."""
+        if self._handle is None:
+            raise capi.MppiError("call warp_setup() first")
+        if self._terrain_dirty:
+            self._push_terrain()
+        pj = capi.PROJ_3D if proj == "3d" else capi.PROJ_2D
+        st = self._state()
+        self._stream = torch.cuda.current_stream(self.device).cuda_stream
+        noise = self._injected_noise.data_ptr() if self._injected_noise is not None else None
+        offset = self._step_count
+        capi.check(self._lib.mppi_step(self._handle, C.byref(st), pj, noise, self.seed, offset, self._stream),
+                   "mppi_step")
+        self._last_state, self._last_proj, self._last_offset = st, pj, offset
+        self._step_count += 1
+        self._sim_stale = True
+
+    def step_command(self, proj="3d"):
+        """MPPI_step + read-back of the command (v*[0], w*[0]) in one library call (8-byte pinned D2H):
+        what the driver does with MPPI_step and two `.numpy()[0]` reads (driver :468-472)."""
+        if self._terrain_dirty:
+            self._push_terrain()
+        pj = capi.PROJ_3D if proj == "3d" else capi.PROJ_2D
+        st = self._state()
+        offset = self._step_count
+        self._stream = torch.cuda.current_stream(self.device).cuda_stream
+        capi.check(self._lib.mppi_step_host(self._handle, C.byref(st), pj, self.seed, offset, self._cmd,
+                                            self._stream), "mppi_step_host")
+        self._last_state, self._last_proj, self._last_offset = st, pj, offset
+        self._step_count += 1
+        self._sim_stale = True
+        return float(self._cmd[0]), float(self._cmd[1])
+
+    def _ensure_sim(self):
+        """Launch 9 of the reference (optimal-trajectory rollout, MPPI_isaac.py:696-720), computed lazily."""
+        if self._sim_stale and self._last_state is not None:
+            capi.check(self._lib.mppi_sim_rollout(self._handle, C.byref(self._last_state), self._stream),
+                       "mppi_sim_rollout")
+            self._sim_stale = False
+
+    def stats(self) -> dict:
+        s = self._stats.cpu().numpy()
+        i = s.view(np.int32)
+        return dict(min_cost=float(s[0]), argmin=int(i[1]), weights_sum=float(s[2]), oob=int(i[3]), nan=int(i[4]),
+                    ess=float(s[5]), v0=float(s[6]), w0=float(s[7]))
+
+    def debug_dump(self, which=("traj",), replay_last: bool = True) -> dict:
+        """Materialises K x T intermediates of the LAST step on request (the visualiser's `trajectories`,
+        driver :520-528).  Returns torch tensors on the device."""
+        K, T = self.number_of_trajectories, self.number_of_iterations
+        dev = self.device
+        shapes = {"u1": (K, T), "u2": (K, T), "v": (K, T), "w": (K, T), "traj": (K, T, 3), "heading": (K, T, 3),
+                  "lw": (K, T, 3), "rw": (K, T, 3), "dem_ij": (K, T, 2), "lw_ij": (K, T, 2), "rw_ij": (K, T, 2),
+                  "cm_ij": (K, T, 2), "critics": (K, 4), "weights": (K,)}
+        d = capi.MppiDebugDump()
+        out = {}
+        for name in which:
+            dt = torch.int32 if name.endswith("_ij") else torch.float32
+            out[name] = torch.zeros(shapes[name], dtype=dt, device=dev)
+            setattr(d, name, out[name].data_ptr())
+        st = self._last_state if (replay_last and self._last_state is not None) else self._state()
+        noise = self._injected_noise.data_ptr() if self._injected_noise is not None else None
+        capi.check(self._lib.mppi_debug_dump(self._handle, C.byref(st), self._last_proj, noise, self.seed,
+                                             self._last_offset, 1 if replay_last else 0, C.byref(d), self._stream),
+                   "mppi_debug_dump")
+        return out
+
+    @property
+    def trajectories(self):
+        """K*T x 3 sampled trajectories of the last step (MPPI_isaac.py:467), materialised on access."""
+        K, T = self.number_of_trajectories, self.number_of_iterations
+        return DeviceArray(self.debug_dump(("traj",))["traj"].reshape(K * T, 3))
+
+    # ------------------------------------------------------------------ offline closed loop
+    def run(self, proj="3d", max_loops: int = 3500):
+        """Closed loop with the controller's own model as the plant, MPPI_isaac.py:755-805."""
+        self.warp_setup()
+        while (abs(self.robot.x[-1] - self.goal_x) > 0.5 or abs(self.robot.y[-1] - self.goal_y) > 0.5) \
+                and self.loop < max_loops:
+            self.reset("controller")
+            self.MPPI_step(proj=proj)
+            traj0 = self.trajectories_sim.numpy()[0]
+            head0 = self.heading_vectors_sim.numpy()[0]
+            self.robot.update_position(float(traj0[0]), float(traj0[1]), float(traj0[2]), head0.astype(np.float64))
+            lin_vel = float(self.optimal_lin_vel_wp.numpy()[0])
+            ang_vel = float(self.optimal_ang_vel_wp.numpy()[0])
+            self.std_dev_u1 = np.maximum(0.4, 0.4 - ang_vel * ang_vel)          # MPPI_isaac.py:777-778
+            self.std_dev_u2 = np.maximum(0.4, 0.4 + ang_vel * ang_vel)
+            self.robot.lin_vel.append(lin_vel)
+            self.robot.ang_vel.append(ang_vel)
+            self.robot.left_wheel_speed = lin_vel - ang_vel * self.robot.radius / 2
+            self.robot.right_wheel_speed = lin_vel + ang_vel * self.robot.radius / 2
+            self.loop += 1
+        return self.loop
+
+    def close(self):
+        if self._handle is not None:
+            self._lib.mppi_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

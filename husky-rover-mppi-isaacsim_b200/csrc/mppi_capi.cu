@@ -1,0 +1,373 @@
+// mppi_capi.cu -- C ABI of libmppi_b200.so (include/mppi_b200.h): handle management and launch plumbing.
+// Host side only; all arithmetic lives in mppi_kernels.cu.  No torch types, no CPU fallback: every entry
+// that computes needs a CUDA device and fails with MPPI_ERR_CUDA otherwise.
+#include "mppi_kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace mppi;
+
+struct MppiHandle {
+    MppiParams p;
+    int device;
+    int max_rovers;
+    int K_cap, T_cap;
+    int block, nblocks;
+    bool has_terrain;
+    MppiTerrain terrain;
+    const MppiTerrain* terrains_dev;
+    int n_terrains;
+    // device buffers
+    float *nominal1, *nominal2, *prev1, *prev2, *opt_v, *opt_w, *costs, *partials, *stats, *sim_traj, *sim_heading;
+    float* dbg_costs;
+    unsigned int* counters;
+    float* cmd_pinned;      // host pinned [2]
+    cudaEvent_t ev0, ev1;
+    bool timing;
+    bool timed_valid;
+};
+
+static thread_local char g_cuda_err[256];
+
+static int cuda_fail(cudaError_t e, const char* where)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "CUDA error at %s: %s", where, cudaGetErrorString(e));
+    return MPPI_ERR_CUDA;
+}
+#define CK(call)                                         \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+extern "C" const char* mppi_strerror(int status)
+{
+    switch (status) {
+    case MPPI_OK: return "ok";
+    case MPPI_ERR_INVALID_ARG: return "invalid argument";
+    case MPPI_ERR_CUDA: return g_cuda_err[0] ? g_cuda_err : "CUDA error";
+    case MPPI_ERR_NO_TERRAIN: return "terrain not set (call mppi_set_terrain first)";
+    case MPPI_ERR_ALLOC: return "allocation failed";
+    case MPPI_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+    }
+}
+
+extern "C" int mppi_abi_version(void) { return MPPI_B200_ABI_VERSION; }
+
+extern "C" int mppi_default_params(MppiParams* p, int32_t K, int32_t T)
+{
+    if (!p || K <= 0 || T < 2) return MPPI_ERR_INVALID_ARG;
+    memset(p, 0, sizeof(*p));
+    p->K = K; p->T = T; p->math = MPPI_MATH_STRICT;
+    p->dt = 0.045f;
+    p->u1_min = -1.f; p->u1_max = 1.f; p->u2_min = -1.f; p->u2_max = 1.f;
+    p->v_min = 0.f; p->v_max = 2.f; p->w_min = -1.f; p->w_max = 1.f;
+    p->lambda = 0.3f; p->r_wheels = 1.2f;
+    p->filt_k = 3.5f; p->filt_a = 0.96f; p->opt_k = 3.0f; p->opt_a = 0.92f;
+    p->wheel_offset = 0.2f;
+    p->cw_path = 100.5f; p->cw_slope = 50.5f; p->cw_speed = 0.5f; p->cw_obs = 25.0f;
+    p->lethal_thresh = 0.99f; p->lethal_penalty = 100000.0f;
+    p->near_goal_cut = 2.0f; p->speed_eps = 0.0001f; p->pf_eps = 1e-6f; p->pf_near_gain = 10.0f;
+    p->slope_eps = 1e-6f; p->slope_gain = 5.0f;
+    p->horizon = (float)(0.045 * 2.0 * (double)T);
+    p->target_speed = 2.0f;
+    return MPPI_OK;
+}
+
+// Block size: small K is latency-bound (one warp per SM is ideal), large K wants full CTAs.
+static void pick_launch(int K, int T, int* block, int* nblocks)
+{
+    int b;
+    if (K <= 148 * 32 * 2) b = 32;
+    else if (K <= 148 * 64 * 8) b = 64;
+    else b = 128;
+    while ((K + b - 1) / b > 8192 && b < kMaxBlock) b *= 2;
+    (void)T;
+    *block = b;
+    *nblocks = (K + b - 1) / b;
+}
+
+static bool params_ok(const MppiParams* p)
+{
+    return p && p->K > 0 && p->T >= 2 && p->T <= 512 && p->lambda > 0.f && p->dt > 0.f &&
+           (p->math == MPPI_MATH_STRICT || p->math == MPPI_MATH_FAST);
+}
+
+extern "C" int mppi_create(const MppiParams* params, int32_t device, int32_t max_rovers, MppiHandle** out)
+{
+    if (!out || !params_ok(params) || max_rovers < 1) return MPPI_ERR_INVALID_ARG;
+    CK(cudaSetDevice(device));
+    MppiHandle* h = new (std::nothrow) MppiHandle();
+    if (!h) return MPPI_ERR_ALLOC;
+    memset(h, 0, sizeof(*h));
+    h->p = *params; h->device = device; h->max_rovers = max_rovers;
+    h->K_cap = params->K; h->T_cap = params->T;
+    pick_launch(params->K, params->T, &h->block, &h->nblocks);
+    if ((size_t)h->nblocks > 8192) { delete h; return MPPI_ERR_UNSUPPORTED; }
+    const size_t R = (size_t)max_rovers, T = (size_t)params->T, K = (size_t)params->K;
+    const size_t stride = (size_t)partial_stride(params->T);
+    // worst-case block count over the launch configs we may pick (block >= 32)
+    const size_t nb_cap = (K + 31) / 32;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](float** p, size_t n) { if (e == cudaSuccess) { e = cudaMalloc((void**)p, n * sizeof(float)); if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(float)); } };
+    alloc(&h->nominal1, R * T); alloc(&h->nominal2, R * T);
+    alloc(&h->prev1, R * T); alloc(&h->prev2, R * T);
+    alloc(&h->opt_v, R * T); alloc(&h->opt_w, R * T);
+    alloc(&h->costs, R * K);
+    alloc(&h->partials, R * nb_cap * stride);
+    alloc(&h->stats, R * kStatsStride);
+    alloc(&h->sim_traj, 3 * T); alloc(&h->sim_heading, 3 * T);
+    alloc(&h->dbg_costs, K);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->counters, R * kCounterStride * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(h->counters, 0, R * kCounterStride * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->cmd_pinned, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) { mppi_destroy(h); return cuda_fail(e, "mppi_create"); }
+    *out = h;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_destroy(MppiHandle* h)
+{
+    if (!h) return MPPI_OK;
+    cudaSetDevice(h->device);
+    float* bufs[] = { h->nominal1, h->nominal2, h->prev1, h->prev2, h->opt_v, h->opt_w, h->costs, h->partials,
+                      h->stats, h->sim_traj, h->sim_heading, h->dbg_costs };
+    for (float* b : bufs) if (b) cudaFree(b);
+    if (h->counters) cudaFree(h->counters);
+    if (h->cmd_pinned) cudaFreeHost(h->cmd_pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_set_params(MppiHandle* h, const MppiParams* params)
+{
+    if (!h || !params_ok(params) || params->K > h->K_cap || params->T > h->T_cap) return MPPI_ERR_INVALID_ARG;
+    h->p = *params;
+    pick_launch(params->K, params->T, &h->block, &h->nblocks);
+    return MPPI_OK;
+}
+
+static bool terrain_ok(const MppiTerrain* t)
+{
+    return t && t->dem && t->costmap && t->grid_size >= 2 && t->costmap_size >= 1 && t->resolution > 0.f &&
+           t->costmap_resolution > 0.f;
+}
+
+extern "C" int mppi_set_terrain(MppiHandle* h, const MppiTerrain* terrain)
+{
+    if (!h || !terrain_ok(terrain)) return MPPI_ERR_INVALID_ARG;
+    h->terrain = *terrain;
+    h->has_terrain = true;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_set_terrain_batched(MppiHandle* h, const MppiTerrain* terrains_dev, int32_t n_rovers)
+{
+    if (!h || !terrains_dev || n_rovers < 1 || n_rovers > h->max_rovers) return MPPI_ERR_INVALID_ARG;
+    h->terrains_dev = terrains_dev;
+    h->n_terrains = n_rovers;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_set_nominal(MppiHandle* h, const float* u1, const float* u2, int32_t n_rovers, void* stream)
+{
+    if (!h || !u1 || !u2 || n_rovers < 1 || n_rovers > h->max_rovers) return MPPI_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)n_rovers * h->p.T * sizeof(float);
+    CK(cudaMemcpyAsync(h->nominal1, u1, n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->nominal2, u2, n, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    return MPPI_OK;
+}
+
+extern "C" int mppi_get_nominal(MppiHandle* h, float* u1, float* u2, int32_t n_rovers, void* stream)
+{
+    if (!h || !u1 || !u2 || n_rovers < 1 || n_rovers > h->max_rovers) return MPPI_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)n_rovers * h->p.T * sizeof(float);
+    CK(cudaMemcpyAsync(u1, h->nominal1, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(u2, h->nominal2, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return MPPI_OK;
+}
+
+static int do_step(MppiHandle* h, const MppiState* state, const MppiState* states_dev, int n_rovers, int proj,
+                   const float* noise, uint64_t seed, uint64_t offset, uint32_t k_begin, float* rank_partial,
+                   cudaStream_t s)
+{
+    if (!h || (proj != MPPI_PROJ_2D && proj != MPPI_PROJ_3D)) return MPPI_ERR_INVALID_ARG;
+    if (!state && !states_dev) return MPPI_ERR_INVALID_ARG;
+    if (states_dev) {
+        if (!h->terrains_dev || n_rovers > h->n_terrains) return MPPI_ERR_NO_TERRAIN;
+    } else if (!h->has_terrain) {
+        return MPPI_ERR_NO_TERRAIN;
+    }
+    CK(cudaSetDevice(h->device));
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = h->p;
+    if (state) a.state = *state;
+    a.terrain = h->terrain;
+    a.states = states_dev;
+    a.terrains = states_dev ? h->terrains_dev : nullptr;
+    a.noise = noise;
+    a.nominal1 = h->nominal1; a.nominal2 = h->nominal2; a.prev1 = h->prev1; a.prev2 = h->prev2;
+    a.opt_v = h->opt_v; a.opt_w = h->opt_w; a.costs = h->costs; a.partials = h->partials; a.stats = h->stats;
+    a.counters = h->counters;
+    a.rank_partial = rank_partial;
+    a.seed = seed; a.offset = offset; a.k_begin = k_begin; a.nblocks = h->nblocks;
+    if (h->timing) CK(cudaEventRecord(h->ev0, s));
+    cudaError_t e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_fused(a, proj, n_rovers, h->block, s)
+                                                  : strict::launch_fused(a, proj, n_rovers, h->block, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_fused");
+    if (h->timing) { CK(cudaEventRecord(h->ev1, s)); h->timed_valid = true; }
+    return MPPI_OK;
+}
+
+extern "C" int mppi_step(MppiHandle* h, const MppiState* state, int32_t proj, const float* noise_dev,
+                         uint64_t seed, uint64_t offset, void* stream)
+{
+    if (!state) return MPPI_ERR_INVALID_ARG;
+    return do_step(h, state, nullptr, 1, proj, noise_dev, seed, offset, 0u, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int mppi_step_host(MppiHandle* h, const MppiState* state, int32_t proj, uint64_t seed, uint64_t offset,
+                              float* cmd_host, void* stream)
+{
+    if (!state || !cmd_host) return MPPI_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = do_step(h, state, nullptr, 1, proj, nullptr, seed, offset, 0u, nullptr, s);
+    if (rc != MPPI_OK) return rc;
+    CK(cudaMemcpyAsync(h->cmd_pinned, h->stats + 6, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    cmd_host[0] = h->cmd_pinned[0];
+    cmd_host[1] = h->cmd_pinned[1];
+    return MPPI_OK;
+}
+
+extern "C" int mppi_step_batched(MppiHandle* h, const MppiState* states_dev, int32_t n_rovers, int32_t proj,
+                                 uint64_t seed, uint64_t offset, void* stream)
+{
+    if (!h || !states_dev || n_rovers < 1 || n_rovers > h->max_rovers) return MPPI_ERR_INVALID_ARG;
+    return do_step(h, nullptr, states_dev, n_rovers, proj, nullptr, seed, offset, 0u, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int mppi_partial_floats(int32_t T) { return partial_stride(T); }
+
+extern "C" int mppi_step_partial(MppiHandle* h, const MppiState* state, int32_t proj, const float* noise_dev,
+                                 uint64_t seed, uint64_t offset, uint32_t k_begin, float* partial_dev, void* stream)
+{
+    if (!state || !partial_dev) return MPPI_ERR_INVALID_ARG;
+    return do_step(h, state, nullptr, 1, proj, noise_dev, seed, offset, k_begin, partial_dev, (cudaStream_t)stream);
+}
+
+extern "C" int mppi_combine_partials(MppiHandle* h, const MppiState* state, const float* partials_dev,
+                                     int32_t n_parts, void* stream)
+{
+    if (!h || !state || !partials_dev || n_parts < 1 || n_parts > 8192) return MPPI_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CombineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = h->p; a.state = *state; a.parts = partials_dev; a.n_parts = n_parts;
+    a.nominal1 = h->nominal1; a.nominal2 = h->nominal2; a.prev1 = h->prev1; a.prev2 = h->prev2;
+    a.opt_v = h->opt_v; a.opt_w = h->opt_w; a.stats = h->stats;
+    cudaError_t e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_combine(a, (cudaStream_t)stream)
+                                                  : strict::launch_combine(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_combine");
+    return MPPI_OK;
+}
+
+extern "C" int mppi_sim_rollout(MppiHandle* h, const MppiState* state, void* stream)
+{
+    if (!h || !state) return MPPI_ERR_INVALID_ARG;
+    if (!h->has_terrain) return MPPI_ERR_NO_TERRAIN;
+    CK(cudaSetDevice(h->device));
+    SimArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = h->p; a.state = *state; a.terrain = h->terrain;
+    a.opt_v = h->opt_v; a.opt_w = h->opt_w; a.sim_traj = h->sim_traj; a.sim_heading = h->sim_heading;
+    cudaError_t e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_sim(a, (cudaStream_t)stream)
+                                                  : strict::launch_sim(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_sim");
+    return MPPI_OK;
+}
+
+extern "C" int mppi_debug_dump(MppiHandle* h, const MppiState* state, int32_t proj, const float* noise_dev,
+                               uint64_t seed, uint64_t offset, int32_t use_previous_nominal,
+                               const MppiDebugDump* dump, void* stream)
+{
+    if (!h || !state || !dump || (proj != MPPI_PROJ_2D && proj != MPPI_PROJ_3D)) return MPPI_ERR_INVALID_ARG;
+    if (!h->has_terrain) return MPPI_ERR_NO_TERRAIN;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    DumpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = h->p; a.state = *state; a.terrain = h->terrain; a.noise = noise_dev;
+    a.nominal1 = use_previous_nominal ? h->prev1 : h->nominal1;
+    a.nominal2 = use_previous_nominal ? h->prev2 : h->nominal2;
+    a.d = *dump; a.costs = h->dbg_costs; a.seed = seed; a.offset = offset; a.k_begin = 0u;
+    const bool fastm = (h->p.math == MPPI_MATH_FAST);
+    cudaError_t e = fastm ? fast::launch_dump(a, proj, s) : strict::launch_dump(a, proj, s);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_dump");
+    if (dump->weights) {
+        e = fastm ? fast::launch_weights(h->dbg_costs, h->p.K, h->p.lambda, dump->weights, s)
+                  : strict::launch_weights(h->dbg_costs, h->p.K, h->p.lambda, dump->weights, s);
+        if (e != cudaSuccess) return cuda_fail(e, "launch_weights");
+    }
+    return MPPI_OK;
+}
+
+extern "C" int mppi_get_outputs(MppiHandle* h, MppiOutputs* out)
+{
+    if (!h || !out) return MPPI_ERR_INVALID_ARG;
+    out->optimal_u1 = h->nominal1; out->optimal_u2 = h->nominal2;
+    out->optimal_v = h->opt_v; out->optimal_w = h->opt_w;
+    out->costs = h->costs; out->stats = h->stats;
+    out->sim_traj = h->sim_traj; out->sim_heading = h->sim_heading;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_enable_timing(MppiHandle* h, int32_t on)
+{
+    if (!h) return MPPI_ERR_INVALID_ARG;
+    h->timing = on != 0;
+    h->timed_valid = false;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_last_step_us(MppiHandle* h, float* us)
+{
+    if (!h || !us || !h->timed_valid) return MPPI_ERR_INVALID_ARG;
+    CK(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *us = ms * 1000.f;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_test_detmath(int32_t fn, const float* x, float* y0, float* y1, int32_t n, void* stream)
+{
+    if (!x || !y0 || n < 1 || fn < 0 || fn > 3) return MPPI_ERR_INVALID_ARG;
+    cudaError_t e = strict::launch_detmath(fn, x, y0, y1, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_detmath");
+    return MPPI_OK;
+}
+
+extern "C" int mppi_test_noise(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k_begin, int32_t K, int32_t T,
+                               int32_t math, float* e1, float* e2, void* stream)
+{
+    if (!e1 || !e2 || K < 1 || T < 1) return MPPI_ERR_INVALID_ARG;
+    cudaError_t e = (math == MPPI_MATH_FAST) ? fast::launch_noise(seed, offset, rover, k_begin, K, T, e1, e2, (cudaStream_t)stream)
+                                             : strict::launch_noise(seed, offset, rover, k_begin, K, T, e1, e2, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_noise");
+    return MPPI_OK;
+}

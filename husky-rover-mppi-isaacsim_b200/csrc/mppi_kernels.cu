@@ -1,0 +1,579 @@
+// mppi_kernels.cu -- the fused MPPI iteration for sm_100a.
+//
+// One launch replaces launches 1-8 of MPPI_Controller.MPPI_step (MPPI_isaac.py:512-692):
+//   phase 1  one thread per sample: Philox noise (or injected eps) -> u -> wheel filter -> rollout on the
+//            DEM -> streaming critics -> cost[k].  No K x T tensor is written.
+//   phase 2  per block: min/argmin, w = exp(-(c - m_b)/lambda), sum w, and A[t] = sum_k w_k u[k,t] where u is
+//            REGENERATED from the counter-based noise only for samples with w > 0 (a zero weight adds
+//            exactly +0, so skipping is bit-exact).  One softmax partial per block goes to global memory.
+//   phase 3  the last block to finish (atomic ticket) folds the partials in block order (deterministic
+//            online softmax), writes the updated nominal, runs the (opt_k, opt_a) wheel filter and
+//            publishes (v*, w*).  In sample-sharded multi-GPU mode it writes the rank partial instead.
+//
+// Compiled twice: STRICT (-fmad=false ...) and FAST (-DMPPI_FLAVOR_FAST -use_fast_math).
+#include "mppi_kernels.cuh"
+#include "mppi_device.cuh"
+
+#include <math_constants.h>
+
+namespace mppi {
+namespace MPPI_NS {
+
+// ------------------------------------------------------------------ block-level helpers
+__device__ __forceinline__ void pair_min(float& c, int& k, float oc, int ok)
+{
+    if (oc < c || (oc == c && ok < k)) { c = oc; k = ok; }
+}
+
+__device__ __forceinline__ void warp_min(float& c, int& k)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float oc = __shfl_xor_sync(0xffffffffu, c, off);
+        const int ok = __shfl_xor_sync(0xffffffffu, k, off);
+        pair_min(c, k, oc, ok);
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Shared-memory carve-up (floats).  `nblocks` only matters for the block that runs phase 3.
+struct Smem {
+    float* nom1;        // [T]
+    float* nom2;        // [T]
+    float* red_f;       // [3 * 32] warp partials
+    int* red_i;         // [2 * 32]
+    int* list_i;        // [max(B, nblocks)]  compacted sample / block indices
+    float* list_w;      // [max(B, nblocks)]  their weights / scales
+    float* acc;         // [4 * B] group accumulators, later new nominal [2T]
+};
+
+__host__ __device__ inline size_t smem_floats(int T, int B, int nblocks)
+{
+    const int L = (B > nblocks) ? B : nblocks;
+    const int accn = (4 * B > 2 * T) ? 4 * B : 2 * T;
+    return (size_t)2 * T + 96 + 64 + 2 * (size_t)L + accn;
+}
+
+__device__ __forceinline__ Smem carve(float* base, int T, int B, int nblocks)
+{
+    const int L = (B > nblocks) ? B : nblocks;
+    Smem s;
+    s.nom1 = base;
+    s.nom2 = s.nom1 + T;
+    s.red_f = s.nom2 + T;
+    s.red_i = reinterpret_cast<int*>(s.red_f + 96);
+    s.list_i = s.red_i + 64;
+    s.list_w = reinterpret_cast<float*>(s.list_i + L);
+    s.acc = s.list_w + L;
+    return s;
+}
+
+// Block-wide (min, argmin) with ties to the lowest index; result broadcast to all threads.
+__device__ __forceinline__ void block_min(float& c, int& k, const Smem& s)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    warp_min(c, k);
+    __syncthreads();
+    if (lane == 0) { s.red_f[warp] = c; s.red_i[warp] = k; }
+    __syncthreads();
+    c = s.red_f[0]; k = s.red_i[0];
+    for (int w = 1; w < nw; ++w) pair_min(c, k, s.red_f[w], s.red_i[w]);
+}
+
+// Block-wide sums of two values in a fixed order; broadcast.
+__device__ __forceinline__ void block_sum2(float& a, float& b, const Smem& s)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { s.red_f[32 + warp] = a; s.red_f[64 + warp] = b; }
+    __syncthreads();
+    a = s.red_f[32]; b = s.red_f[64];
+    for (int w = 1; w < nw; ++w) { a += s.red_f[32 + w]; b += s.red_f[64 + w]; }
+}
+
+// Ordered compaction of the threads with `keep` into (list_i, list_w), appended at `base`.
+// Returns the new element count (uniform).
+__device__ __forceinline__ int block_compact(bool keep, int idx, float val, int base, const Smem& s)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    __syncthreads();
+    if (lane == 0) s.red_i[32 + warp] = __popc(mask);
+    __syncthreads();
+    int off = base, total = base;
+    for (int w = 0; w < nw; ++w) {
+        const int c = s.red_i[32 + w];
+        if (w < warp) off += c;
+        total += c;
+    }
+    if (keep) {
+        const int pos = off + __popc(mask & ((1u << lane) - 1u));
+        s.list_i[pos] = idx;
+        s.list_w[pos] = val;
+    }
+    return total;
+}
+
+// ------------------------------------------------------------------ phase 3: fold partials, finish the update
+// parts: [n][stride] softmax partials (read through L2).  Called by ONE block; smem nom1/nom2 hold the old nominal.
+__device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, const float* parts, int n,
+                                     const Smem& s, float* nominal1, float* nominal2, float* prev1, float* prev2,
+                                     float* opt_v, float* opt_w, float* stats, float* rank_partial,
+                                     unsigned oob_count, unsigned nan_count)
+{
+    const int T = p.T, tid = threadIdx.x, B = blockDim.x;
+    const int stride = partial_stride(T);
+
+    // 1. global min / argmin (ties -> lowest sample id)
+    float M = CUDART_INF_F;
+    int arg = 0x7fffffff;
+    for (int b = tid; b < n; b += B) {
+        const float mb = __ldcg(parts + (size_t)b * stride);
+        const int kb = __float_as_int(__ldcg(parts + (size_t)b * stride + 2));
+        pair_min(M, arg, mb, kb);
+    }
+    block_min(M, arg, s);
+
+    // 2. scale of every partial relative to M; keep the non-zero ones, in order
+    int cnt = 0;
+    for (int base = 0; base < n; base += B) {
+        const int b = base + tid;
+        float sc = 0.0f;
+        if (b < n) sc = fexp(fdiv(-(__ldcg(parts + (size_t)b * stride) - M), p.lambda));
+        cnt = block_compact(sc > 0.0f, b, sc, cnt, s);
+    }
+    __syncthreads();
+
+    // 3. ordered fold; every thread recomputes S (identical on all threads), thread j < 2T owns column j
+    float S = 0.0f, S2 = 0.0f;
+    for (int col0 = 0; col0 < 2 * T; col0 += B) {
+        const int col = col0 + tid;
+        float acc = 0.0f;
+        S = 0.0f; S2 = 0.0f;
+        for (int e = 0; e < cnt; ++e) {
+            const float* pb = parts + (size_t)s.list_i[e] * stride;
+            const float sc = s.list_w[e];
+            S += __ldcg(pb + 1) * sc;
+            S2 += __ldcg(pb + 3) * sc * sc;
+            if (col < 2 * T) acc += __ldcg(pb + kPartialHeader + col) * sc;
+        }
+        if (col < 2 * T) s.acc[col] = acc;
+    }
+    __syncthreads();
+
+    if (rank_partial != nullptr) {           // sample-sharded mode: publish {M, S, argmin, S2, A1, A2}
+        if (tid == 0) {
+            rank_partial[0] = M; rank_partial[1] = S; rank_partial[2] = __int_as_float(arg); rank_partial[3] = S2;
+        }
+        for (int col = tid; col < 2 * T; col += B) rank_partial[kPartialHeader + col] = s.acc[col];
+        return;
+    }
+
+    // 4. updated nominal = A / S  (critics_warp.py:363-376); keep the previous one for replay
+    for (int col = tid; col < 2 * T; col += B) {
+        const float nv = fdiv(s.acc[col], S);
+        s.acc[col] = nv;
+        if (col < T) { prev1[col] = s.nom1[col]; nominal1[col] = nv; }
+        else { prev2[col - T] = s.nom2[col - T]; nominal2[col - T] = nv; }
+    }
+    __syncthreads();
+
+    // 5. optimal sequence -> (v*, w*) with (opt_k, opt_a), sequential in t (MPPI_isaac.py:672-692)
+    if (tid == 0) {
+        float l = st.wheel_l, r = st.wheel_r;
+        const float oma = 1.0f - p.opt_a;
+        float v0 = 0.f, w0 = 0.f;
+        for (int t = 0; t < T; ++t) {
+            l = l * p.opt_a + s.acc[t] * p.opt_k * oma;
+            r = r * p.opt_a + s.acc[T + t] * p.opt_k * oma;
+            const float v = clampf((l + r) / 2.0f, p.v_min, p.v_max);
+            const float w = clampf(fdiv(-l + r, p.r_wheels), p.w_min, p.w_max);
+            opt_v[t] = v; opt_w[t] = w;
+            if (t == 0) { v0 = v; w0 = w; }
+        }
+        stats[0] = M;
+        stats[1] = __int_as_float(arg);
+        stats[2] = S;
+        stats[3] = __uint_as_float(oob_count);
+        stats[4] = __uint_as_float(nan_count);
+        stats[5] = fdiv(S * S, S2);           // effective sample size
+        stats[6] = v0;                         // the command, contiguous for one 8-byte D2H
+        stats[7] = w0;
+    }
+}
+
+// ------------------------------------------------------------------ the fused kernel
+template <int PROJ, bool INJECT>
+__global__ void __launch_bounds__(kMaxBlock)
+mppi_fused_kernel(const __grid_constant__ FusedArgs A)
+{
+    extern __shared__ float smem_raw[];
+    const MppiParams& p = A.p;
+    const int T = p.T, K = p.K, B = blockDim.x, tid = threadIdx.x;
+    const int rover = blockIdx.y;
+    const Smem s = carve(smem_raw, T, B, A.nblocks);
+
+    const MppiState st = (A.states != nullptr) ? A.states[rover] : A.state;
+    const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
+    const Terr ter = make_terr(tr);
+    const SampleConsts sc = make_consts(p, st);
+    const NoiseKey nk = make_noise_key(A.seed, A.offset, (uint32_t)rover);
+
+    float* nominal1 = A.nominal1 + (size_t)rover * T;
+    float* nominal2 = A.nominal2 + (size_t)rover * T;
+    for (int t = tid; t < T; t += B) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
+    __syncthreads();
+
+    const int k_local = blockIdx.x * B + tid;
+    const bool valid = k_local < K;
+    const uint32_t kg = A.k_begin + (uint32_t)k_local;
+    const float* eps1 = INJECT ? A.noise + ((size_t)rover * 2 * K + k_local) * T : nullptr;
+    const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
+
+    // ---------------- phase 1: rollout + critics
+    float cost = CUDART_INF_F;
+    unsigned my_oob = 0, my_nan = 0;
+    if (valid) {
+        SampleAcc a;
+        sample_init<PROJ>(st, ter, a);
+        const DumpPtrs nod = {};
+        for (int t = 0; t < T; t += 2) {
+            float e1a, e1b, e2a, e2b;
+            if (INJECT) {
+                e1a = eps1[t]; e2a = eps2[t];
+                e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
+                e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
+            } else {
+                noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
+            }
+            {
+                const float u1 = sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
+                const float u2 = sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
+                sample_step<PROJ, false>(p, st, ter, sc, a, t, u1, u2, nod, 0);
+            }
+            if (t + 1 < T) {
+                const float u1 = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
+                const float u2 = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
+                sample_step<PROJ, false>(p, st, ter, sc, a, t + 1, u1, u2, nod, 0);
+            }
+        }
+        cost = sample_cost(p, sc, a, nullptr);
+        A.costs[(size_t)rover * K + k_local] = cost;
+        my_oob = (unsigned)a.oob;
+        if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }   // a NaN rollout gets zero weight
+    }
+    if (my_oob) atomicAdd(&A.counters[rover * kCounterStride + 1], my_oob);
+    if (my_nan) atomicAdd(&A.counters[rover * kCounterStride + 2], my_nan);
+
+    // ---------------- phase 2: block softmax partial
+    float m_b = cost;
+    int arg_b = valid ? (int)kg : 0x7fffffff;
+    block_min(m_b, arg_b, s);
+    float w = 0.0f;
+    if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));   // critics_warp.py:346-347
+    float s_b = w, s2_b = w * w;
+    block_sum2(s_b, s2_b, s);
+    const int n_e = block_compact(w > 0.0f, tid, w, 0, s);
+    __syncthreads();
+
+    const int stride = partial_stride(T);
+    float* part = A.partials + ((size_t)rover * A.nblocks + blockIdx.x) * stride;
+    {
+        const int P = (T + 1) >> 1;                       // step pairs
+        const int G = (B >= 2 * P) ? B / P : 1;           // entry groups working in parallel
+        const int g = tid / P, pr0 = tid - g * P;
+        for (int pbase = 0; pbase < P; pbase += B) {      // one pass unless P > B
+            const int pr = (G > 1) ? pr0 : pbase + tid;
+            const bool active = (G > 1) ? (g < G) : (pr < P);
+            float a1a = 0.f, a1b = 0.f, a2a = 0.f, a2b = 0.f;
+            if (active) {
+                const int t = 2 * pr;
+                for (int e = (G > 1) ? g : 0; e < n_e; e += G) {
+                    const int kl = blockIdx.x * B + s.list_i[e];
+                    const float we = s.list_w[e];
+                    float e1a, e1b, e2a, e2b;
+                    if (INJECT) {
+                        const float* q1 = A.noise + ((size_t)rover * 2 * K + kl) * T;
+                        const float* q2 = q1 + (size_t)K * T;
+                        e1a = q1[t]; e2a = q2[t];
+                        e1b = (t + 1 < T) ? q1[t + 1] : 0.f;
+                        e2b = (t + 1 < T) ? q2[t + 1] : 0.f;
+                    } else {
+                        noise_pair(nk, A.k_begin + (uint32_t)kl, (uint32_t)pr, e1a, e1b, e2a, e2b);
+                    }
+                    a1a += we * sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
+                    a2a += we * sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
+                    if (t + 1 < T) {
+                        a1b += we * sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
+                        a2b += we * sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
+                    }
+                }
+            }
+            if (G > 1) {                                  // fold the groups in order
+                __syncthreads();
+                if (active) {
+                    float* q = s.acc + 4 * (g * P + pr);
+                    q[0] = a1a; q[1] = a1b; q[2] = a2a; q[3] = a2b;
+                }
+                __syncthreads();
+                if (tid < P) {
+                    a1a = a1b = a2a = a2b = 0.f;
+                    for (int gg = 0; gg < G; ++gg) {
+                        const float* q = s.acc + 4 * (gg * P + tid);
+                        a1a += q[0]; a1b += q[1]; a2a += q[2]; a2b += q[3];
+                    }
+                }
+            }
+            const bool writer = (G > 1) ? (tid < P) : active;
+            const int prw = (G > 1) ? tid : pr;
+            if (writer) {
+                const int t = 2 * prw;
+                part[kPartialHeader + t] = a1a;
+                part[kPartialHeader + T + t] = a2a;
+                if (t + 1 < T) { part[kPartialHeader + t + 1] = a1b; part[kPartialHeader + T + t + 1] = a2b; }
+            }
+            if (G > 1) break;
+        }
+    }
+    if (tid == 0) { part[0] = m_b; part[1] = s_b; part[2] = __int_as_float(arg_b); part[3] = s2_b; }
+
+    // ---------------- phase 3: last block folds everything
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned ticket = atomicAdd(&A.counters[rover * kCounterStride + 0], 1u);
+        s.red_i[63] = (ticket == (unsigned)(A.nblocks - 1));
+    }
+    __syncthreads();
+    if (!s.red_i[63]) return;
+    __threadfence();
+
+    const unsigned oob_count = __ldcg(&A.counters[rover * kCounterStride + 1]);
+    const unsigned nan_count = __ldcg(&A.counters[rover * kCounterStride + 2]);
+    combine_and_finalize(p, st, A.partials + (size_t)rover * A.nblocks * stride, A.nblocks, s,
+                         nominal1, nominal2, A.prev1 + (size_t)rover * T, A.prev2 + (size_t)rover * T,
+                         A.opt_v + (size_t)rover * T, A.opt_w + (size_t)rover * T,
+                         A.stats + (size_t)rover * kStatsStride,
+                         A.rank_partial ? A.rank_partial + (size_t)rover * stride : nullptr, oob_count, nan_count);
+    if (tid == 0) {                                       // re-arm for the next launch
+        A.counters[rover * kCounterStride + 0] = 0u;
+        A.counters[rover * kCounterStride + 1] = 0u;
+        A.counters[rover * kCounterStride + 2] = 0u;
+    }
+}
+
+// ------------------------------------------------------------------ rank-partial combine (multi-GPU epilogue)
+__global__ void __launch_bounds__(kMaxBlock) mppi_combine_kernel(const __grid_constant__ CombineArgs A)
+{
+    extern __shared__ float smem_raw[];
+    const int T = A.p.T, B = blockDim.x;
+    const Smem s = carve(smem_raw, T, B, A.n_parts);
+    for (int t = threadIdx.x; t < T; t += B) { s.nom1[t] = A.nominal1[t]; s.nom2[t] = A.nominal2[t]; }
+    __syncthreads();
+    combine_and_finalize(A.p, A.state, A.parts, A.n_parts, s, A.nominal1, A.nominal2, A.prev1, A.prev2,
+                         A.opt_v, A.opt_w, A.stats, nullptr, 0u, 0u);
+}
+
+// ------------------------------------------------------------------ validation / visualiser dump (unfused view)
+template <int PROJ, bool INJECT>
+__global__ void __launch_bounds__(128) mppi_dump_kernel(const __grid_constant__ DumpArgs A)
+{
+    const MppiParams& p = A.p;
+    const int T = p.T, K = p.K;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const Terr ter = make_terr(A.terrain);
+    const SampleConsts sc = make_consts(p, A.state);
+    const NoiseKey nk = make_noise_key(A.seed, A.offset, 0u);
+    DumpPtrs d;
+    d.u1 = A.d.u1; d.u2 = A.d.u2; d.v = A.d.v; d.w = A.d.w;
+    d.traj = A.d.traj; d.heading = A.d.heading; d.lw = A.d.lw; d.rw = A.d.rw;
+    d.dem_ij = A.d.dem_ij; d.lw_ij = A.d.lw_ij; d.rw_ij = A.d.rw_ij; d.cm_ij = A.d.cm_ij;
+    SampleAcc a;
+    sample_init<PROJ>(A.state, ter, a);
+    const float* eps1 = INJECT ? A.noise + (size_t)k * T : nullptr;
+    const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
+    for (int t = 0; t < T; t += 2) {
+        float e1a, e1b, e2a, e2b;
+        if (INJECT) {
+            e1a = eps1[t]; e2a = eps2[t];
+            e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
+            e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
+        } else {
+            noise_pair(nk, A.k_begin + (uint32_t)k, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
+        }
+        {
+            const float u1 = sample_u(A.nominal1, t, T, A.state.sigma1, e1a, p.u1_min, p.u1_max);
+            const float u2 = sample_u(A.nominal2, t, T, A.state.sigma2, e2a, p.u2_min, p.u2_max);
+            sample_step<PROJ, true>(p, A.state, ter, sc, a, t, u1, u2, d, (size_t)k * T + t);
+        }
+        if (t + 1 < T) {
+            const float u1 = sample_u(A.nominal1, t + 1, T, A.state.sigma1, e1b, p.u1_min, p.u1_max);
+            const float u2 = sample_u(A.nominal2, t + 1, T, A.state.sigma2, e2b, p.u2_min, p.u2_max);
+            sample_step<PROJ, true>(p, A.state, ter, sc, a, t + 1, u1, u2, d, (size_t)k * T + t + 1);
+        }
+    }
+    float cr[4];
+    const float cost = sample_cost(p, sc, a, cr);
+    if (A.costs) A.costs[k] = cost;
+    if (A.d.critics) { for (int i = 0; i < 4; ++i) A.d.critics[4 * k + i] = cr[i]; }
+}
+
+// weights with the global minimum, as the reference intends (critics_warp.py:338-347, run_mppi.py:222-226)
+__global__ void __launch_bounds__(1024) mppi_weights_kernel(const float* costs, int K, float lambda, float* weights)
+{
+    __shared__ float red[32];
+    float m = CUDART_INF_F;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) m = fminf(m, costs[k]);
+    for (int off = 16; off > 0; off >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w) m = fminf(m, red[w]);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) weights[k] = fexp(fdiv(-(costs[k] - m), lambda));
+}
+
+// optimal-trajectory rollout, dim = 1 (MPPI_isaac.py:696-720): always the 3-D kernel, driven by (v*, w*)
+__global__ void mppi_sim_kernel(const __grid_constant__ SimArgs A)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const MppiParams& p = A.p;
+    const Terr ter = make_terr(A.terrain);
+    int oob = 0, i, j;
+    float x = A.state.x, y = A.state.y;
+    Quad q = corners(ter, x, y, i, j, oob);
+    float3 n = normal_on_grid(q, ter.res);
+    float3 prev = tangent(n, make_float3(A.state.hx, A.state.hy, A.state.hz));
+    for (int t = 0; t < p.T; ++t) {
+        update_position(x, y, prev, A.opt_v[t], p.dt);
+        q = corners(ter, x, y, i, j, oob);
+        const float h = bilinear(x, y, q, ter.res);
+        n = normal_on_grid(q, ter.res);
+        prev = tangent(n, prev);
+        const float3 cur = update_orientation(prev, A.opt_w[t], n, p.dt);
+        A.sim_traj[3 * t] = x; A.sim_traj[3 * t + 1] = y; A.sim_traj[3 * t + 2] = h;
+        A.sim_heading[3 * t] = cur.x; A.sim_heading[3 * t + 1] = cur.y; A.sim_heading[3 * t + 2] = cur.z;
+        prev = cur;
+    }
+}
+
+// ------------------------------------------------------------------ test hooks
+__global__ void mppi_detmath_kernel(int fn, const float* x, float* y0, float* y1, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.f, b = 0.f;
+    switch (fn) {
+    case 0: dm::sincosf_det(x[i], a, b); break;
+    case 1: dm::sincos2pif_det(x[i], a, b); break;
+    case 2: a = dm::logf_det(x[i]); break;
+    default: a = dm::expf_det(x[i]); break;
+    }
+    y0[i] = a;
+    if (y1) y1[i] = b;
+}
+
+__global__ void mppi_noise_kernel(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k_begin, int K, int T,
+                                  float* e1, float* e2)
+{
+    const int P = (T + 1) >> 1;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)K * P) return;
+    const int k = (int)(idx / P), pr = (int)(idx - (size_t)k * P);
+    const NoiseKey nk = make_noise_key(seed, offset, rover);
+    float a0, a1, b0, b1;
+    noise_pair(nk, k_begin + (uint32_t)k, (uint32_t)pr, a0, a1, b0, b1);
+    const int t = 2 * pr;
+    e1[(size_t)k * T + t] = a0; e2[(size_t)k * T + t] = b0;
+    if (t + 1 < T) { e1[(size_t)k * T + t + 1] = a1; e2[(size_t)k * T + t + 1] = b1; }
+}
+
+// ------------------------------------------------------------------ launchers
+size_t fused_smem_bytes(int T, int block, int nblocks) { return smem_floats(T, block, nblocks) * sizeof(float); }
+
+template <typename Kern>
+static cudaError_t ensure_smem(Kern k, size_t bytes)
+{
+    if (bytes > 48 * 1024) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, cudaStream_t s)
+{
+    const dim3 grid(a.nblocks, n_rovers);
+    const size_t smem = fused_smem_bytes(a.p.T, block, a.nblocks);
+    cudaError_t e;
+#define MPPI_LAUNCH_FUSED(PROJ, INJ)                                              \
+    do {                                                                          \
+        e = ensure_smem(mppi_fused_kernel<PROJ, INJ>, smem);                      \
+        if (e != cudaSuccess) return e;                                           \
+        mppi_fused_kernel<PROJ, INJ><<<grid, block, smem, s>>>(a);                \
+    } while (0)
+    if (proj == MPPI_PROJ_3D) {
+        if (a.noise) MPPI_LAUNCH_FUSED(MPPI_PROJ_3D, true); else MPPI_LAUNCH_FUSED(MPPI_PROJ_3D, false);
+    } else {
+        if (a.noise) MPPI_LAUNCH_FUSED(MPPI_PROJ_2D, true); else MPPI_LAUNCH_FUSED(MPPI_PROJ_2D, false);
+    }
+#undef MPPI_LAUNCH_FUSED
+    return cudaGetLastError();
+}
+
+cudaError_t launch_combine(const CombineArgs& a, cudaStream_t s)
+{
+    const int block = 256;
+    const size_t smem = fused_smem_bytes(a.p.T, block, a.n_parts);
+    cudaError_t e = ensure_smem(mppi_combine_kernel, smem);
+    if (e != cudaSuccess) return e;
+    mppi_combine_kernel<<<1, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dump(const DumpArgs& a, int proj, cudaStream_t s)
+{
+    const int block = 128, grid = (a.p.K + block - 1) / block;
+    if (proj == MPPI_PROJ_3D) {
+        if (a.noise) mppi_dump_kernel<MPPI_PROJ_3D, true><<<grid, block, 0, s>>>(a);
+        else mppi_dump_kernel<MPPI_PROJ_3D, false><<<grid, block, 0, s>>>(a);
+    } else {
+        if (a.noise) mppi_dump_kernel<MPPI_PROJ_2D, true><<<grid, block, 0, s>>>(a);
+        else mppi_dump_kernel<MPPI_PROJ_2D, false><<<grid, block, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_weights(const float* costs, int K, float lambda, float* weights, cudaStream_t s)
+{
+    mppi_weights_kernel<<<1, 1024, 0, s>>>(costs, K, lambda, weights);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sim(const SimArgs& a, cudaStream_t s)
+{
+    mppi_sim_kernel<<<1, 32, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detmath(int fn, const float* x, float* y0, float* y1, int n, cudaStream_t s)
+{
+    mppi_detmath_kernel<<<(n + 255) / 256, 256, 0, s>>>(fn, x, y0, y1, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_noise(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k_begin, int K, int T,
+                         float* e1, float* e2, cudaStream_t s)
+{
+    const size_t n = (size_t)K * ((T + 1) / 2);
+    mppi_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seed, offset, rover, k_begin, K, T, e1, e2);
+    return cudaGetLastError();
+}
+
+}  // namespace MPPI_NS
+}  // namespace mppi

@@ -1,0 +1,88 @@
+// mppi_kernels.cuh -- host-visible launch interface of the kernel translation units.
+// mppi_kernels.cu is compiled twice (STRICT and FAST arithmetic flavours, see mppi_device.cuh); each
+// compilation exports one set of launchers in its own namespace.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mppi_b200.h"
+
+namespace mppi {
+
+// Softmax partial: {min cost M, sum w, argmin (int bits), sum w^2, A1[T], A2[T]} with w = exp(-(c - M)/lambda)
+// and A = sum_k w_k u[k, t].  Same layout for block partials, rank partials and the all-gather payload.
+constexpr int kPartialHeader = 4;
+__host__ __device__ inline int partial_stride(int T) { return kPartialHeader + 2 * T; }
+
+constexpr int kMaxBlock = 256;        // threads per block upper bound
+constexpr int kStatsStride = 8;       // floats per rover in the stats buffer
+constexpr int kCounterStride = 4;     // uints per rover: {ticket, oob, nan, 0}
+
+struct FusedArgs {
+    MppiParams p;
+    MppiState state;                  // used when states == nullptr
+    MppiTerrain terrain;              // used when terrains == nullptr
+    const MppiState* states;          // device [n_rovers] (batched mode)
+    const MppiTerrain* terrains;      // device [n_rovers] (batched mode)
+    const float* noise;               // device [2][K][T] injected eps, or nullptr (Philox)
+    float* nominal1;                  // device [n_rovers][T]  in: nominal, out: updated nominal
+    float* nominal2;
+    float* prev1;                     // device [n_rovers][T]  copy of the nominal before the update
+    float* prev2;
+    float* opt_v;                     // device [n_rovers][T]
+    float* opt_w;
+    float* costs;                     // device [n_rovers][K]
+    float* partials;                  // device [n_rovers][nblocks][stride]
+    float* stats;                     // device [n_rovers][kStatsStride]
+    unsigned int* counters;           // device [n_rovers][kCounterStride]
+    float* rank_partial;              // if non-null: write the rank partial here and skip the update
+    uint64_t seed, offset;
+    uint32_t k_begin;                 // first global sample id of this rank
+    int32_t nblocks;                  // grid.x
+};
+
+struct CombineArgs {
+    MppiParams p;
+    MppiState state;
+    const float* parts;               // device [n_parts][stride]
+    int32_t n_parts;
+    float* nominal1; float* nominal2; float* prev1; float* prev2;
+    float* opt_v; float* opt_w; float* stats;
+};
+
+struct DumpArgs {
+    MppiParams p;
+    MppiState state;
+    MppiTerrain terrain;
+    const float* noise;
+    const float* nominal1; const float* nominal2;   // the nominal to sample around
+    MppiDebugDump d;
+    float* costs;                     // device [K] (debug copy)
+    uint64_t seed, offset;
+    uint32_t k_begin;
+};
+
+struct SimArgs {
+    MppiParams p;
+    MppiState state;
+    MppiTerrain terrain;
+    const float* opt_v; const float* opt_w;
+    float* sim_traj; float* sim_heading;
+};
+
+#define MPPI_DECLARE_LAUNCHERS(NS)                                                                              \
+    namespace NS {                                                                                              \
+    cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, cudaStream_t s);          \
+    cudaError_t launch_combine(const CombineArgs& a, cudaStream_t s);                                          \
+    cudaError_t launch_dump(const DumpArgs& a, int proj, cudaStream_t s);                                      \
+    cudaError_t launch_weights(const float* costs, int K, float lambda, float* weights, cudaStream_t s);      \
+    cudaError_t launch_sim(const SimArgs& a, cudaStream_t s);                                                  \
+    cudaError_t launch_detmath(int fn, const float* x, float* y0, float* y1, int n, cudaStream_t s);          \
+    cudaError_t launch_noise(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k_begin, int K, int T,  \
+                             float* e1, float* e2, cudaStream_t s);                                            \
+    size_t fused_smem_bytes(int T, int block, int nblocks);                                                    \
+    }
+
+MPPI_DECLARE_LAUNCHERS(strict)
+MPPI_DECLARE_LAUNCHERS(fast)
+
+}  // namespace mppi

@@ -1,0 +1,194 @@
+/*
+ * mppi_b200.h -- C ABI of libmppi_b200.so: the B200-native (sm_100a) MPPI controller core.
+ *
+ * Drop-in boundary.  The reference has no FFI: its boundary is the Python class
+ * `MPPI_Controller` (thesis_master/warp_implementation/MPPI_isaac.py:402-805) whose methods issue
+ * nine `wp.launch` calls per control iteration (MPPI_isaac.py:505-720).  Each entry point below
+ * names the reference interface it replaces.  All pointers are plain device or host pointers as
+ * documented; no torch / Warp types cross this boundary.  Every function returns an int status
+ * (0 = MPPI_OK, negative = error; see mppi_strerror).
+ *
+ * Threading: a handle is thread-compatible (one thread at a time).  All device work is issued
+ * asynchronously on the `stream` argument (a cudaStream_t passed as void*; NULL = legacy default
+ * stream) unless stated otherwise.
+ */
+#ifndef MPPI_B200_H
+#define MPPI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPPI_B200_ABI_VERSION 1
+
+enum {
+    MPPI_OK = 0,
+    MPPI_ERR_INVALID_ARG = -1,
+    MPPI_ERR_CUDA = -2,
+    MPPI_ERR_NO_TERRAIN = -3,
+    MPPI_ERR_ALLOC = -4,
+    MPPI_ERR_UNSUPPORTED = -5
+};
+
+enum { MPPI_PROJ_2D = 2, MPPI_PROJ_3D = 3 };   /* MPPI_step(proj="2d"|"3d")  MPPI_isaac.py:554,578 */
+
+/* Arithmetic flavour of the kernels.
+ *  STRICT: every fp32 operation in reference order, no FMA contraction, IEEE div/sqrt, specified
+ *          ("det") sin/cos/exp/log -> bit-identical to oracle/mppi_oracle.c in MATH_DET mode.
+ *  FAST:   FMA contraction + approximate reciprocal/rsqrt/MUFU intrinsics (throughput mode; matches the
+ *          oracle within tolerance, not bit-for-bit). */
+enum { MPPI_MATH_STRICT = 0, MPPI_MATH_FAST = 1 };
+
+/* Every tunable / literal of the reference hot path. Defaults via mppi_default_params. */
+typedef struct MppiParams {
+    int32_t K;              /* number_of_trajectories                       config.yaml:7   */
+    int32_t T;              /* number_of_iterations (horizon steps), 2..512  config.yaml:5   */
+    int32_t math;           /* MPPI_MATH_*                                                   */
+    int32_t reserved0;
+    float dt;               /* config.yaml:6 */
+    float u1_min, u1_max, u2_min, u2_max;       /* config.yaml:21-24 */
+    float v_min, v_max, w_min, w_max;           /* config.yaml:11-12,15-16 */
+    float lambda;           /* temperature config.yaml:28 */
+    float r_wheels;         /* robot.radius used as track width  MPPI_isaac.py:537 */
+    float filt_k, filt_a;   /* sample wheel filter  (3.5, 0.96)  MPPI_isaac.py:548-549 */
+    float opt_k, opt_a;     /* optimal-sequence filter (3.0, 0.92) MPPI_isaac.py:688-689 */
+    float wheel_offset;     /* 0.2 m  projection_warp.py:333 */
+    float cw_path, cw_slope, cw_speed, cw_obs;  /* 100.5, 50.5, 0.5, 25  critics_warp.py:325-329 */
+    float lethal_thresh, lethal_penalty;        /* 0.99, 1e5  critics_warp.py:251-252 */
+    float near_goal_cut;    /* 2.0   critics_warp.py:285 */
+    float speed_eps;        /* 1e-4  critics_warp.py:297 */
+    float pf_eps;           /* 1e-6  critics_warp.py:111 */
+    float pf_near_gain;     /* 10.0  critics_warp.py:126 */
+    float slope_eps;        /* 1e-6  critics_warp.py:188 */
+    float slope_gain;       /* 5.0   critics_warp.py:209-210 */
+    float horizon;          /* dt*v_max*T  MPPI_isaac.py:440 (host double -> float) */
+    float target_speed;     /* v_max_linear MPPI_isaac.py:619 */
+} MppiParams;
+
+/* Terrain = DEM `Z_wp` + obstacle `costmap_wp` (MPPI_isaac.py:463-464), borrowed device pointers. */
+typedef struct MppiTerrain {
+    const float *dem;       /* device, row-major [grid_size*grid_size]; row 0 at y=+half_width (projection_warp.py:40) */
+    int32_t grid_size;
+    float half_width;       /* x_min = y_min = -half_width  MPPI_isaac.py:584-585 */
+    float resolution;       /* 2*half_width/grid_size  MPPI_isaac.py:265 */
+    const float *costmap;   /* device, row-major [costmap_size*costmap_size]  critics_warp.py:248 */
+    int32_t costmap_size;
+    float costmap_resolution; /* 2*half_width/costmap_size MPPI_isaac.py:272 */
+} MppiTerrain;
+
+/* Per-iteration inputs the caller mutates between steps (visual_terrain_stack_full_terrain.py:494-515,
+ * 574-576; MPPI_isaac.py:769-784). */
+typedef struct MppiState {
+    float x, y;             /* robot.x[-1], robot.y[-1] */
+    float hx, hy, hz;       /* robot.heading_vector / |.|  (MPPI_isaac.py:493) */
+    float wheel_l, wheel_r; /* robot.left/right_wheel_speed */
+    float sigma1, sigma2;   /* std_dev_u1 / std_dev_u2 */
+    float goal_x, goal_y, goal_theta;
+} MppiState;
+
+/* Device-resident results of the last step (pointers owned by the handle, valid until mppi_destroy). */
+typedef struct MppiOutputs {
+    const float *optimal_u1, *optimal_u2;   /* [T]  optimal_u1_wp / optimal_u2_wp (= next nominal) */
+    const float *optimal_v, *optimal_w;     /* [T]  optimal_lin_vel_wp / optimal_ang_vel_wp; [0] is the command */
+    const float *costs;                     /* [n_rovers*K] costs_wp */
+    const float *stats;                     /* [n_rovers*8] {min_cost, argmin(int bits), weights_sum, oob_count(int bits),
+                                                nan_count(int bits), ess, 0, 0} */
+    const float *sim_traj, *sim_heading;    /* [T*3] trajectories_sim / heading_vectors_sim (after mppi_sim_rollout) */
+} MppiOutputs;
+
+/* Optional dump of the K x T intermediates (validation / visualiser only; the fused step never
+ * materialises them).  Any pointer may be NULL.  Layouts match the reference arrays. */
+typedef struct MppiDebugDump {
+    float *u1, *u2, *v, *w;                 /* device [K*T]   u1,u2 (MPPI_isaac.py:448-449), linear/angular_velocities */
+    float *traj, *heading, *lw, *rw;        /* device [K*T*3] trajectories, heading_vectors, left/right_wheel_pos */
+    int32_t *dem_ij, *lw_ij, *rw_ij;        /* device [K*T*2] DEM cell (i, j) of body / left / right wheel */
+    int32_t *cm_ij;                         /* device [K*T*2] costmap cell (ix, iy) */
+    float *critics;                         /* device [K*4]   path, slope, speed, obstacle (unweighted) */
+    float *weights;                         /* device [K]     exp(-(c-min)/lambda) with the global min */
+} MppiDebugDump;
+
+typedef struct MppiHandle MppiHandle;
+
+const char *mppi_strerror(int status);
+int mppi_abi_version(void);
+
+/* Fills *p with the reference defaults (config.yaml + kernel literals) for the given K, T. */
+int mppi_default_params(MppiParams *p, int32_t K, int32_t T);
+
+/* Replaces MPPI_Controller.__init__ + warp_setup (MPPI_isaac.py:404-487): allocates all device scratch
+ * for up to `max_rovers` independent controllers (1 for the reference use). Nominal sequences start at 0
+ * (MPPI_isaac.py:446-447). */
+int mppi_create(const MppiParams *params, int32_t device, int32_t max_rovers, MppiHandle **out);
+int mppi_destroy(MppiHandle *h);
+int mppi_set_params(MppiHandle *h, const MppiParams *params);   /* K, T must not exceed the created sizes */
+
+/* Replaces `Z_wp = ...` / `costmap_wp.assign(...)` (MPPI_isaac.py:463-464, driver :561-567).
+ * Pointers are borrowed (zero-copy) and must stay valid while steps run. */
+int mppi_set_terrain(MppiHandle *h, const MppiTerrain *terrain);
+/* Batched mode: terrains_dev = device array [n_rovers] of MppiTerrain (per-rover maps). */
+int mppi_set_terrain_batched(MppiHandle *h, const MppiTerrain *terrains_dev, int32_t n_rovers);
+
+/* optimal_u1_wp / optimal_u2_wp accessors (host pointers, [n_rovers*T]); synchronous on `stream`. */
+int mppi_set_nominal(MppiHandle *h, const float *u1_host, const float *u2_host, int32_t n_rovers, void *stream);
+int mppi_get_nominal(MppiHandle *h, float *u1_host, float *u2_host, int32_t n_rovers, void *stream);
+
+/* Replaces reset("controller") + MPPI_step(proj) launches 1-8 (MPPI_isaac.py:489-692): ONE fused kernel
+ * (sample -> wheel filter -> rollout on the DEM -> critics -> online softmax -> update -> (v*, w*)).
+ *  noise_dev: NULL = production mode, counter-based Philox4x32-10 keyed by (seed, offset, sample id);
+ *             else device [2][K][T] standard-normal eps injected in validation mode (shared-noise parity).
+ *  Asynchronous on `stream`. */
+int mppi_step(MppiHandle *h, const MppiState *state, int32_t proj, const float *noise_dev,
+              uint64_t seed, uint64_t offset, void *stream);
+
+/* Same, then copies the command (v*[0], w*[0]) to cmd_host[2] and synchronises: the call the reference
+ * driver makes as MPPI_step + 2 x `.numpy()[0]` (visual_terrain_stack_full_terrain.py:468-472). */
+int mppi_step_host(MppiHandle *h, const MppiState *state, int32_t proj, uint64_t seed, uint64_t offset,
+                   float *cmd_host, void *stream);
+
+/* Multi-rover batch (BASELINE config 4): n_rovers independent controllers, states_dev = device [n_rovers]
+ * MppiState, terrains from mppi_set_terrain_batched. Rover r uses Philox stream (seed, offset, rover=r). */
+int mppi_step_batched(MppiHandle *h, const MppiState *states_dev, int32_t n_rovers, int32_t proj,
+                      uint64_t seed, uint64_t offset, void *stream);
+
+/* Sample-sharded multi-GPU mode (BASELINE config 3): this rank rolls out global samples
+ * [k_begin, k_begin + params.K) and writes its softmax partial {M, S, argmin(int bits), A1[T], A2[T]}
+ * (3 + 2T floats) to partial_dev instead of updating the nominal.  After the ranks exchange partials
+ * (one all-gather), mppi_combine_partials folds `n_parts` partials in rank order -- identically on every
+ * rank -- and finishes the update (nominal, v*, w*). */
+int mppi_step_partial(MppiHandle *h, const MppiState *state, int32_t proj, const float *noise_dev,
+                      uint64_t seed, uint64_t offset, uint32_t k_begin, float *partial_dev, void *stream);
+int mppi_combine_partials(MppiHandle *h, const MppiState *state, const float *partials_dev, int32_t n_parts,
+                          void *stream);
+int mppi_partial_floats(int32_t T);   /* 3 + 2T */
+
+/* Replaces launch 9 (MPPI_isaac.py:696-720): rollout of the optimal sequence (dim = 1) from `state`,
+ * filling sim_traj / sim_heading. Lazy: only run() consumes element [0] (MPPI_isaac.py:769-772). */
+int mppi_sim_rollout(MppiHandle *h, const MppiState *state, void *stream);
+
+/* Validation / visualiser path: re-runs sampling + rollout + critics for rover 0 and writes the requested
+ * K x T intermediates (what the unfused reference keeps in `trajectories`, `left_wheel_pos`, ...). Uses the
+ * nominal sequence as it was BEFORE the last step when `use_previous_nominal` != 0. */
+int mppi_debug_dump(MppiHandle *h, const MppiState *state, int32_t proj, const float *noise_dev,
+                    uint64_t seed, uint64_t offset, int32_t use_previous_nominal,
+                    const MppiDebugDump *dump, void *stream);
+
+int mppi_get_outputs(MppiHandle *h, MppiOutputs *out);
+
+/* Last measured device time of mppi_step* in microseconds (CUDA events on the step's stream); optional
+ * profiling aid, enabled with mppi_enable_timing(h, 1). Synchronises the stream. */
+int mppi_enable_timing(MppiHandle *h, int32_t on);
+int mppi_last_step_us(MppiHandle *h, float *us);
+
+/* Test hook: evaluates the specified ("det") math on the device. fn: 0 sincos, 1 sincos(2*pi*u), 2 log, 3 exp.
+ * x, y0, y1 are device pointers [n]. */
+int mppi_test_detmath(int32_t fn, const float *x_dev, float *y0_dev, float *y1_dev, int32_t n, void *stream);
+/* Test hook: Philox normals exactly as the production kernel draws them -> eps1/eps2 device [K*T]. */
+int mppi_test_noise(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k_begin, int32_t K, int32_t T,
+                    int32_t math, float *eps1_dev, float *eps2_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPI_B200_H */

@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- MPPI hot-path benchmark (one JSON line on stdout, contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C5] [--math strict|fast]
+  python bench.py --impl reference ...        # CPU port of the reference path on the host cores
+
+A "step" is one full control iteration (sample -> wheel filter -> rollout on the DEM -> critics -> softmax
+update -> (v*, w*)) of ONE fused kernel launch over synthetic terrain of the BASELINE.json shape.
+N = 1 runs BASELINE config 2 (K = 4096, T = 100, 1500^2 DEM, 750^2 costmap).  N > 1 keeps that per-GPU
+workload (weak scaling): one logical controller with N x 4096 samples, sample-sharded, whose only exchange
+is an all-gather of the 816-byte softmax partial followed by the same deterministic combine on every rank.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE_STEP = 230.0      # SURVEY.md Appendix B (3-D skid-steer path)
+GATHER_BYTES_PER_SAMPLE_STEP = 28.0   # 7 gathered fp32 words (4 DEM corners + 2 wheel cells + 1 costmap cell)
+STATE_BYTES = 48                  # sizeof(MppiState): the per-step host input
+CMD_BYTES = 8                     # (v*[0], w*[0]) read back per step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--math", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed iterations")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+def build_workload(name):
+    from mppi_b200 import synthetic as syn
+    w = syn.WORKLOADS[name]
+    dem = syn.crater_dem(w.grid_size, w.half_width).numpy()
+    cm = syn.rock_costmap(w.costmap_size, w.half_width)
+    start, goal = syn.workload_start_goal(w)
+    return w, dem, cm, start, goal
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(w, dem, cm, start, goal, seconds, steps=None, warmup=0, K=None):
+    """Times the C port of the reference path (oracle/mppi_oracle.c, libm math) on all host cores."""
+    from oracle import oracle_c as oc
+    oc.build()
+    K = K or w.K
+    T = w.T
+    threads = oc.num_threads()
+    p = oc.make_params(K=K, T=T, math=oc.MATH_LIBM)
+    st = dict(x=start[0], y=start[1], hx=1.0, hy=0.0, hz=0.0, wheel_l=0.0, wheel_r=0.0, sigma1=0.25, sigma2=0.25,
+              goal_x=goal[0], goal_y=goal[1], goal_theta=2.2)
+    rng = np.random.default_rng(0)
+    e1 = rng.standard_normal((K, T)).astype(np.float32)
+    e2 = rng.standard_normal((K, T)).astype(np.float32)
+    n1 = np.zeros(T, np.float32)
+    n2 = np.zeros(T, np.float32)
+    for _ in range(max(1, warmup)):
+        r = oc.mppi_step(p, dem, w.half_width, cm, st, n1, n2, e1, e2, nthreads=threads)
+    times = []
+    t_end = time.perf_counter() + seconds
+    while (steps is None and time.perf_counter() < t_end) or (steps is not None and len(times) < steps):
+        t0 = time.perf_counter()
+        r = oc.mppi_step(p, dem, w.half_width, cm, st, n1, n2, e1, e2, nthreads=threads)
+        times.append(time.perf_counter() - t0)
+        n1, n2 = r.nominal1, r.nominal2          # closed-loop dependence on the nominal, as on the GPU
+    times = np.array(times)
+    return dict(value=K * T / times.mean(), unit="sample-steps/s", cores=threads, kind="port",
+                sample=f"{len(times)} full iterations of K={K} T={T} (injected noise, sampling excluded), "
+                       f"C port of the reference kernels (oracle/mppi_oracle.c, libm), {threads} pthreads",
+                ms_per_step=float(times.mean() * 1e3), p50_ms=float(np.median(times) * 1e3)), times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, dem, cm, start, goal = build_workload(args.workload)
+    base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "MPPI sample-steps/s", "value": base["value"], "unit": "sample-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name, "K": w.K, "T": w.T, "dem": f"{w.grid_size}x{w.grid_size} f32",
+                   "costmap": f"{w.costmap_size}x{w.costmap_size} f32",
+                   "note": "the reference's GPU path needs NVIDIA Warp (absent, no network); this arm is the C port "
+                           "of its kernels on the host cores"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "latency_us": {"p50": float(np.median(times) * 1e6), "p99": float(np.percentile(times, 99) * 1e6)},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": float(self.max_mhz) if self.max_mhz else None,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mppi_b200 import capi
+    from mppi_b200.core import Core, make_state
+    from mppi_b200.sharding import SampleShardedStepper
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    w, dem_np, cm_np, start, goal = build_workload(args.workload)
+    K, T = w.K, w.T                       # per-GPU samples
+    K_total = K * n_gpus
+    core = Core(K, T, device=local_rank, math=args.math)
+    dem = torch.from_numpy(dem_np).to(dev)
+    cm = torch.from_numpy(cm_np).to(dev)
+    core.set_terrain(dem, w.half_width, cm)
+    state = make_state(start[0], start[1], (1.0, 0.0, 0.0), goal_x=goal[0], goal_y=goal[1])
+    stepper = SampleShardedStepper(core, K_total) if n_gpus > 1 else None
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    do_flush = not args.no_flush
+    seed = 42
+
+    def one_step(i):
+        if stepper is None:
+            core.step(state, capi.PROJ_3D, None, seed, i)
+        else:
+            stepper.step(state, capi.PROJ_3D, seed, i)
+
+    def timed_loop(n, first, flush):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for i in range(n):
+            if flush:
+                flush_buf.fill_(i & 0xff)
+            evs[i][0].record()
+            one_step(first + i)
+            evs[i][1].record()
+        torch.cuda.synchronize(dev)
+        return np.array([a.elapsed_time(b) for a, b in evs], dtype=np.float64)     # ms each
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # warm-up
+    timed_loop(max(3, args.warmup), 0, do_flush)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    per_step_ms = timed_loop(args.steps, 1000, do_flush)
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    total_ms = float(per_step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = K_total * T / (ms_per_step * 1e-3)
+
+    # steady-state (L2 warm) numbers for context
+    warm_ms = timed_loop(args.steps, 5000, False)
+
+    # end-to-end through the host-facing call: host state in, host (v, w) out, D2H + sync inside the timed region
+    e2e = None
+    if n_gpus == 1:
+        for i in range(5):
+            core.step_host(state, capi.PROJ_3D, seed, 9000 + i)
+        e2e_t = []
+        for i in range(args.steps):
+            if do_flush:
+                flush_buf.fill_(i & 0xff)
+                torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            core.step_host(state, capi.PROJ_3D, seed, 10000 + i)
+            e2e_t.append(time.perf_counter() - t0)
+        e2e_t = np.array(e2e_t)
+        e2e = {"value": K * T / float(e2e_t.mean()), "unit": "sample-steps/s", "h2d_bytes_per_step": STATE_BYTES,
+               "d2h_bytes_per_step": CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6),
+               "p99_us": float(np.percentile(e2e_t, 99) * 1e6),
+               "call": "mppi_step_host (C ABI): MppiState by value from host memory, 8-byte pinned D2H of the "
+                       "command, stream synchronise"}
+    else:
+        # the sharded step's result is read back on every rank
+        e2e_t = []
+        for i in range(min(args.steps, 100)):
+            if do_flush:
+                flush_buf.fill_(i & 0xff)
+            barrier()
+            t0 = time.perf_counter()
+            one_step(20000 + i)
+            _ = core.stats[0, 6:8].cpu()
+            e2e_t.append(time.perf_counter() - t0)
+        t = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": K_total * T / float(t.item()), "unit": "sample-steps/s", "h2d_bytes_per_step": STATE_BYTES,
+               "d2h_bytes_per_step": CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6)}
+
+    if rank == 0:
+        pk = peaks()
+        fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12          # TFLOP/s, FFMA
+        achieved_tflops = FLOP_PER_SAMPLE_STEP * K * T / (ms_per_step * 1e-3) / 1e12
+        hbm_achieved = GATHER_BYTES_PER_SAMPLE_STEP * K * T / (ms_per_step * 1e-3) / 1e9
+        roofline = {
+            "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": achieved_tflops / fp32_peak, "traffic": None,
+            "kernel": "mppi_fused_kernel<3D, Philox> (the only kernel of the step)",
+            "peak_source": f"148 SM x 128 FP32 lanes x 2 x sm_max_mhz ({pk['source']} MEASURED_PEAKS.json); "
+                           "MEASURED_PEAKS has no FP32 figure",
+            "note": "the path is a dependent FP32/XU chain with L2/L1 gathers, neither HBM- nor tensor-bound "
+                    "(SURVEY 8d); algorithmic work = 230 FLOP per sample-step",
+            "hbm": {"achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / pk["hbm_gbs"],
+                    "algorithmic_bytes_per_sample_step": GATHER_BYTES_PER_SAMPLE_STEP},
+        }
+        line = {
+            "metric": "MPPI sample-steps/s", "value": value, "unit": "sample-steps/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "K_per_gpu": K, "K_total": K_total, "T": T,
+                       "dem": f"{w.grid_size}x{w.grid_size} f32", "costmap": f"{w.costmap_size}x{w.costmap_size} f32",
+                       "math": args.math, "noise": "in-kernel Philox4x32-10 + Box-Muller", "proj": "3d",
+                       "l2": "flushed between timed iterations (256 MiB fill)" if do_flush else "warm",
+                       "parallelism": "single GPU" if n_gpus == 1 else
+                       f"sample-sharded x{n_gpus}, all-gather of {core.partial_floats() * 4} B softmax partial"},
+            "latency_us": {"p50": float(np.median(per_step_ms) * 1e3), "p99": float(np.percentile(per_step_ms, 99) * 1e3),
+                           "mean": float(per_step_ms.mean() * 1e3)},
+            "warm_l2": {"ms_per_step": float(warm_ms.mean()), "p50_us": float(np.median(warm_ms) * 1e3),
+                        "value": K_total * T / float(warm_ms.mean() * 1e-3)},
+            "e2e": e2e,
+            "gpu_launches": args.steps * (1 if n_gpus == 1 else 2),
+            "roofline": roofline,
+            "clocks": clocks,
+            "wall_s": wall_s,
+            "stats": core.read_stats(),
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            base, _ = cpu_reference_run(w, dem_np, cm_np, start, goal, seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,102 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/mppi_b200.h declares; argument
+validation that needs no device is exercised (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from mppi_b200 import capi
+    capi.build()
+    return capi
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "mppi_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mppi_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(capi):
+    lib = capi.lib()
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in capi.SYMBOLS, f"{n} has no ctypes signature in capi.SYMBOLS"
+    assert sorted(capi.SYMBOLS) == names
+
+
+def test_abi_version_and_strerror(capi):
+    lib = capi.lib()
+    assert lib.mppi_abi_version() == 1
+    assert lib.mppi_strerror(0) == b"ok"
+    assert b"invalid" in lib.mppi_strerror(-1)
+    assert b"terrain" in lib.mppi_strerror(-3)
+
+
+def test_default_params_are_the_reference_values(capi):
+    p = capi.default_params(1000, 100)           # config.yaml + kernel literals
+    got = {f: getattr(p, f) for f, _ in p._fields_}
+    exp = dict(K=1000, T=100, dt=0.045, u1_min=-1, u1_max=1, u2_min=-1, u2_max=1, v_min=0, v_max=2, w_min=-1, w_max=1,
+               lam=0.3, r_wheels=1.2, filt_k=3.5, filt_a=0.96, opt_k=3.0, opt_a=0.92, wheel_offset=0.2, cw_path=100.5,
+               cw_slope=50.5, cw_speed=0.5, cw_obs=25.0, lethal_thresh=0.99, lethal_penalty=1e5, near_goal_cut=2.0,
+               speed_eps=1e-4, pf_eps=1e-6, pf_near_gain=10.0, slope_eps=1e-6, slope_gain=5.0, horizon=9.0,
+               target_speed=2.0)
+    for k, v in exp.items():
+        assert got[k] == pytest.approx(v, rel=1e-6), k
+
+
+def test_struct_layouts_match_the_header(capi):
+    assert C.sizeof(capi.MppiParams) == 4 * 4 + 30 * 4
+    assert C.sizeof(capi.MppiState) == 48
+    assert C.sizeof(capi.MppiTerrain) == 40
+    assert C.sizeof(capi.MppiOutputs) == 8 * 8
+    assert C.sizeof(capi.MppiDebugDump) == 14 * 8
+
+
+def test_argument_validation_without_a_device(capi):
+    lib = capi.lib()
+    assert lib.mppi_default_params(None, 10, 10) == -1
+    p = capi.MppiParams()
+    assert lib.mppi_default_params(C.byref(p), 0, 10) == -1
+    assert lib.mppi_default_params(C.byref(p), 10, 1) == -1
+    assert lib.mppi_partial_floats(100) == 204
+    assert lib.mppi_destroy(None) == 0
+    assert lib.mppi_get_outputs(None, None) == -1
+    h = C.c_void_p()
+    bad = capi.default_params(16, 8)
+    bad.lam = 0.0
+    assert lib.mppi_create(C.byref(bad), 0, 1, C.byref(h)) == -1
+
+
+def test_product_fails_loudly_without_cuda(capi):
+    """No CPU fallback: on a box without a GPU, creating a controller must raise, not silently compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mppi_b200.core import Core
+    with pytest.raises(capi.MppiError):
+        Core(64, 10)
+    lib = capi.lib()
+    h = C.c_void_p()
+    p = capi.default_params(64, 10)
+    rc = lib.mppi_create(C.byref(p), 0, 1, C.byref(h))
+    assert rc == -2 and b"CUDA" in lib.mppi_strerror(rc)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may reference it."""
+    pkg = os.path.join(ROOT, "husky-rover-mppi-isaacsim_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle_c" not in src, f
+                if f.endswith((".cu", ".cuh")):
+                    assert "oracle/" not in src.replace("oracle/mppi_oracle.c", "").replace("oracle/det_math.h", ""), f

@@ -17,10 +17,11 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-def rel_err(a, b):
+def rel_err(a, b, floor=1e-3):
+    """max |a-b| / max(|b|, floor): relative error with an absolute floor for values near zero."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
-    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3)))
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
 
 
 def run_both(oracle, K, T, name="C1", proj=3, state=None, nominal=None, seed=0, math="strict", philox=False,
@@ -64,7 +65,9 @@ def check_strict(ref, got, d, sim):
     assert rel_err(got["weights_sum"], ref.weights_sum) < RTOL
     assert rel_err(got["nominal1"], ref.nominal1) < RTOL and rel_err(got["nominal2"], ref.nominal2) < RTOL
     assert rel_err(got["nominal1"], ref.nominal1_f64) < RTOL and rel_err(got["nominal2"], ref.nominal2_f64) < RTOL
-    assert rel_err(got["opt_v"], ref.opt_v) < RTOL and rel_err(got["opt_w"], ref.opt_w) < RTOL
+    # w* = (r - l)/track is a difference of wheel speeds: its error scales with |l|, |r| ~ |v*|, not with |w*|
+    wheel_scale = max(float(np.abs(ref.opt_v).max()), 1e-3)
+    assert rel_err(got["opt_v"], ref.opt_v) < RTOL and rel_err(got["opt_w"], ref.opt_w, floor=wheel_scale) < RTOL
     assert got["v0"] == got["opt_v"][0] and got["w0"] == got["opt_w"][0]
     assert rel_err(sim[0], ref.sim_traj) < RTOL and rel_err(sim[1], ref.sim_heading) < RTOL
 

@@ -1,0 +1,79 @@
+"""CPU: host-side mirror of the reference interface (Surface / Robot / MPPI_Controller construction, config
+parsing, state packing) and the partitioning helpers."""
+import numpy as np
+import pytest
+
+import mppi_b200
+from mppi_b200 import MPPI_Controller, Robot, Surface, capi, synthetic
+from mppi_b200.sharding import shard_range
+
+
+def test_surface_geometry_follows_the_reference():
+    s = Surface("manual", "", "manual", "", grid_size=400, half_width=20.0, origin=(0.0, 0.0),
+                bumps=[((1.0, 2.0), 2.0, 3.0)], radius_robot=0.3, obstacles=[(3.0, 4.0, 0.5)])
+    assert s.resolution == pytest.approx(0.1) and s.costmap_size == 50 and s.costmap_resolution == pytest.approx(0.8)
+    assert s.Z.shape == (400, 400) and s.costmap.shape == (50, 50)
+    # crater formula MPPI_isaac.py:317-320 at the crater centre: (h - 0.5) - (h + 0.5) = -1
+    x = np.linspace(-20, 20, 400)
+    i, j = np.argmin(np.abs(x - 1.0)), np.argmin(np.abs(x - 2.0))
+    assert s.Z[j, i] == pytest.approx(-1.0, abs=2e-2)
+    assert 0.0 <= s.costmap.min() and s.costmap.max() == pytest.approx(1.0)
+
+
+def test_robot_and_controller_read_the_yaml_schema():
+    r = Robot(1.0, 2.0, [3.0, 4.0, 0.0], mppi_b200.DEFAULT_CONFIG)
+    assert r.radius == 1.2 and np.allclose(r.heading_vector, [0.6, 0.8, 0.0])
+    r.update_position(1.5, 2.5, 0.1, np.array([0.0, 1.0, 0.0]))
+    assert r.x[-1] == 1.5 and r.z[-1] == 0.1
+    s = Surface("", "", "", "", grid_size=64, half_width=3.2, origin=(0, 0), bumps=[], radius_robot=0.3)
+    c = MPPI_Controller(s, r, mppi_b200.DEFAULT_CONFIG, goal_x=5.0, goal_y=6.0, goal_orientation=2.2)
+    assert (c.number_of_trajectories, c.number_of_iterations, c.dt) == (1000, 100, 0.045)
+    assert c.horizon == pytest.approx(9.0) and c.temperature == 0.3
+    p = c._params()
+    assert (p.K, p.T) == (1000, 100) and p.r_wheels == pytest.approx(1.2) and p.horizon == pytest.approx(9.0)
+    st = c._state()
+    assert (st.x, st.y, st.hx, st.hy) == pytest.approx((1.5, 2.5, 0.0, 1.0))
+    assert (st.goal_x, st.goal_y, st.sigma1) == pytest.approx((5.0, 6.0, 0.25))
+    with pytest.raises(capi.MppiError):
+        c.MPPI_step("3d")                      # warp_setup() not called
+    c.reset("controller")                      # no-op, kept for drop-in compatibility
+
+
+def test_reference_config_file_is_accepted_if_present():
+    import os
+    ref = "/root/reference/thesis_master/warp_implementation/config.yaml"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not mounted")
+    r = Robot(0.0, 0.0, [1.0, 0.0, 0.0], ref)
+    s = Surface("", "", "", "", grid_size=64, half_width=3.2, origin=(0, 0), bumps=[], radius_robot=0.3)
+    c = MPPI_Controller(s, r, ref, 1.0, 1.0, 0.0)
+    ours = MPPI_Controller(s, r, mppi_b200.DEFAULT_CONFIG, 1.0, 1.0, 0.0)
+    for k in ("number_of_iterations", "dt", "number_of_trajectories", "std_dev_u1", "std_dev_u2", "temperature",
+              "v_max_linear", "v_min_angular", "min_u1", "max_u2"):
+        assert getattr(c, k) == getattr(ours, k), k
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 4096, 262144, 262147):
+        for world in (1, 2, 3, 4, 8):
+            pieces = [shard_range(total, world, r) for r in range(world)]
+            assert sum(n for _, n in pieces) == total
+            pos = 0
+            for b, n in pieces:
+                assert b == pos
+                pos += n
+            assert max(n for _, n in pieces) - min(n for _, n in pieces) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_synthetic_workloads_have_the_baseline_shapes():
+    w = synthetic.WORKLOADS
+    assert (w["C1"].K, w["C1"].T) == (1024, 50) and (w["C2"].K, w["C2"].T) == (4096, 100)
+    assert (w["C2"].grid_size, w["C2"].costmap_size) == (1500, 750)
+    assert (w["C3"].K, w["C3"].grid_size) == (262144, 2048) and w["C4"].n_rovers == 4096
+    assert (w["C5"].K, w["C5"].T, w["C5"].grid_size) == (65536, 200, 8192)
+    cm = synthetic.rock_costmap(64, 6.4, n_rocks=5, seed=1)
+    assert cm.shape == (64, 64) and cm.dtype == np.float32 and cm.max() == 1.0
+    dem = synthetic.crater_dem(64, 6.4, bumps=[((0.0, 0.0), 1.0, 1.0)])
+    assert tuple(dem.shape) == (64, 64)

@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--math", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "mono", "pipe"], help="fused-kernel variant")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -81,7 +82,7 @@ def cpu_reference_run(w, dem, cm, start, goal, seconds, steps=None, warmup=0, K=
     for _ in range(max(1, warmup)):
         r = oc.mppi_step(p, dem, w.half_width, cm, st, n1, n2, e1, e2, nthreads=threads)
     times = []
-    t_end = time.perf_counter() + seconds
+    t_end = time.perf_counter() + (seconds or 0.0)
     while (steps is None and time.perf_counter() < t_end) or (steps is not None and len(times) < steps):
         t0 = time.perf_counter()
         r = oc.mppi_step(p, dem, w.half_width, cm, st, n1, n2, e1, e2, nthreads=threads)
@@ -187,7 +188,8 @@ def main():
     w, dem_np, cm_np, start, goal = build_workload(args.workload)
     K, T = w.K, w.T                       # per-GPU samples
     K_total = K * n_gpus
-    core = Core(K, T, device=local_rank, math=args.math)
+    core = Core(K, T, device=local_rank, math=args.math,
+                variant={"auto": capi.VARIANT_AUTO, "mono": capi.VARIANT_MONO, "pipe": capi.VARIANT_PIPE}[args.variant])
     dem = torch.from_numpy(dem_np).to(dev)
     cm = torch.from_numpy(cm_np).to(dev)
     core.set_terrain(dem, w.half_width, cm)
@@ -297,7 +299,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "K_per_gpu": K, "K_total": K_total, "T": T,
                        "dem": f"{w.grid_size}x{w.grid_size} f32", "costmap": f"{w.costmap_size}x{w.costmap_size} f32",
-                       "math": args.math, "noise": "in-kernel Philox4x32-10 + Box-Muller", "proj": "3d",
+                       "math": args.math, "variant": args.variant, "noise": "in-kernel Philox4x32-10 + Box-Muller", "proj": "3d",
                        "l2": "flushed between timed iterations (256 MiB fill)" if do_flush else "warm",
                        "parallelism": "single GPU" if n_gpus == 1 else
                        f"sample-sharded x{n_gpus}, all-gather of {core.partial_floats() * 4} B softmax partial"},

@@ -18,13 +18,14 @@ PROJ_2D = 2
 PROJ_3D = 3
 MATH_STRICT = 0
 MATH_FAST = 1
+VARIANT_AUTO, VARIANT_MONO, VARIANT_PIPE = 0, 1, 2
 PARTIAL_HEADER = 4
 STATS_STRIDE = 8
 
 
 class MppiParams(C.Structure):
     _fields_ = [
-        ("K", C.c_int32), ("T", C.c_int32), ("math", C.c_int32), ("reserved0", C.c_int32),
+        ("K", C.c_int32), ("T", C.c_int32), ("math", C.c_int32), ("variant", C.c_int32),
         ("dt", C.c_float),
         ("u1_min", C.c_float), ("u1_max", C.c_float), ("u2_min", C.c_float), ("u2_max", C.c_float),
         ("v_min", C.c_float), ("v_max", C.c_float), ("w_min", C.c_float), ("w_max", C.c_float),

@@ -15,6 +15,7 @@ struct MppiHandle {
     int max_rovers;
     int K_cap, T_cap;
     int block, nblocks;
+    bool pipe;              // warp-specialised variant selected
     bool has_terrain;
     MppiTerrain terrain;
     const MppiTerrain* terrains_dev;
@@ -61,7 +62,7 @@ extern "C" int mppi_default_params(MppiParams* p, int32_t K, int32_t T)
 {
     if (!p || K <= 0 || T < 2) return MPPI_ERR_INVALID_ARG;
     memset(p, 0, sizeof(*p));
-    p->K = K; p->T = T; p->math = MPPI_MATH_STRICT;
+    p->K = K; p->T = T; p->math = MPPI_MATH_STRICT; p->variant = MPPI_VARIANT_AUTO;
     p->dt = 0.045f;
     p->u1_min = -1.f; p->u1_max = 1.f; p->u2_min = -1.f; p->u2_max = 1.f;
     p->v_min = 0.f; p->v_max = 2.f; p->w_min = -1.f; p->w_max = 1.f;
@@ -77,9 +78,14 @@ extern "C" int mppi_default_params(MppiParams* p, int32_t K, int32_t T)
     return MPPI_OK;
 }
 
-// Block size: small K is latency-bound (one warp per SM is ideal), large K wants full CTAs.
-static void pick_launch(int K, int T, int* block, int* nblocks)
+// Variant + block size.  Small K is latency-bound: the warp-specialised kernel (32 samples per 4-warp CTA) wins
+// while the grid fits the machine a few times over; large K wants the monolithic kernel with full CTAs.
+static void pick_launch(const MppiParams& p, int* block, int* nblocks, bool* pipe)
 {
+    const int K = p.K, T = p.T;
+    const bool can_pipe = true;
+    *pipe = can_pipe && (p.variant == MPPI_VARIANT_PIPE || (p.variant == MPPI_VARIANT_AUTO && K <= 148 * 32 * 4));
+    if (*pipe) { *block = 128; *nblocks = (K + 31) / 32; return; }
     int b;
     if (K <= 148 * 32 * 2) b = 32;
     else if (K <= 148 * 64 * 8) b = 64;
@@ -93,7 +99,7 @@ static void pick_launch(int K, int T, int* block, int* nblocks)
 static bool params_ok(const MppiParams* p)
 {
     return p && p->K > 0 && p->T >= 2 && p->T <= 512 && p->lambda > 0.f && p->dt > 0.f &&
-           (p->math == MPPI_MATH_STRICT || p->math == MPPI_MATH_FAST);
+           (p->math == MPPI_MATH_STRICT || p->math == MPPI_MATH_FAST) && p->variant >= 0 && p->variant <= 2;
 }
 
 extern "C" int mppi_create(const MppiParams* params, int32_t device, int32_t max_rovers, MppiHandle** out)
@@ -105,7 +111,7 @@ extern "C" int mppi_create(const MppiParams* params, int32_t device, int32_t max
     memset(h, 0, sizeof(*h));
     h->p = *params; h->device = device; h->max_rovers = max_rovers;
     h->K_cap = params->K; h->T_cap = params->T;
-    pick_launch(params->K, params->T, &h->block, &h->nblocks);
+    pick_launch(*params, &h->block, &h->nblocks, &h->pipe);
     if ((size_t)h->nblocks > 8192) { delete h; return MPPI_ERR_UNSUPPORTED; }
     const size_t R = (size_t)max_rovers, T = (size_t)params->T, K = (size_t)params->K;
     const size_t stride = (size_t)partial_stride(params->T);
@@ -150,7 +156,7 @@ extern "C" int mppi_set_params(MppiHandle* h, const MppiParams* params)
 {
     if (!h || !params_ok(params) || params->K > h->K_cap || params->T > h->T_cap) return MPPI_ERR_INVALID_ARG;
     h->p = *params;
-    pick_launch(params->K, params->T, &h->block, &h->nblocks);
+    pick_launch(*params, &h->block, &h->nblocks, &h->pipe);
     return MPPI_OK;
 }
 
@@ -226,8 +232,13 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     a.rank_partial = rank_partial;
     a.seed = seed; a.offset = offset; a.k_begin = k_begin; a.nblocks = h->nblocks;
     if (h->timing) CK(cudaEventRecord(h->ev0, s));
-    cudaError_t e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_fused(a, proj, n_rovers, h->block, s)
-                                                  : strict::launch_fused(a, proj, n_rovers, h->block, s);
+    cudaError_t e;
+    if (h->pipe)
+        e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_fused_pipe(a, proj, n_rovers, s)
+                                          : strict::launch_fused_pipe(a, proj, n_rovers, s);
+    else
+        e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_fused(a, proj, n_rovers, h->block, s)
+                                          : strict::launch_fused(a, proj, n_rovers, h->block, s);
     if (e != cudaSuccess) return cuda_fail(e, "launch_fused");
     if (h->timing) { CK(cudaEventRecord(h->ev1, s)); h->timed_valid = true; }
     return MPPI_OK;

@@ -210,66 +210,17 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
     }
 }
 
-// ------------------------------------------------------------------ the fused kernel
-template <int PROJ, bool INJECT>
-__global__ void __launch_bounds__(kMaxBlock)
-mppi_fused_kernel(const __grid_constant__ FusedArgs A)
+// ------------------------------------------------------------------ phases 2 + 3, shared by both fused kernels
+// Every thread of the block calls this.  `valid` threads own one sample each (local index `k_in_block`, cost
+// `cost`); `spb` = samples per block.  INJECT: u is re-read from the injected noise instead of regenerated.
+template <bool INJECT>
+__device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState& st, const NoiseKey& nk, const Smem& s,
+                                             int rover, int spb, bool valid, int k_in_block, float cost,
+                                             unsigned my_oob, unsigned my_nan, float* nominal1, float* nominal2)
 {
-    extern __shared__ float smem_raw[];
     const MppiParams& p = A.p;
     const int T = p.T, K = p.K, B = blockDim.x, tid = threadIdx.x;
-    const int rover = blockIdx.y;
-    const Smem s = carve(smem_raw, T, B, A.nblocks);
-
-    const MppiState st = (A.states != nullptr) ? A.states[rover] : A.state;
-    const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
-    const Terr ter = make_terr(tr);
-    const SampleConsts sc = make_consts(p, st);
-    const NoiseKey nk = make_noise_key(A.seed, A.offset, (uint32_t)rover);
-
-    float* nominal1 = A.nominal1 + (size_t)rover * T;
-    float* nominal2 = A.nominal2 + (size_t)rover * T;
-    for (int t = tid; t < T; t += B) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
-    __syncthreads();
-
-    const int k_local = blockIdx.x * B + tid;
-    const bool valid = k_local < K;
-    const uint32_t kg = A.k_begin + (uint32_t)k_local;
-    const float* eps1 = INJECT ? A.noise + ((size_t)rover * 2 * K + k_local) * T : nullptr;
-    const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
-
-    // ---------------- phase 1: rollout + critics
-    float cost = CUDART_INF_F;
-    unsigned my_oob = 0, my_nan = 0;
-    if (valid) {
-        SampleAcc a;
-        sample_init<PROJ>(st, ter, a);
-        const DumpPtrs nod = {};
-        for (int t = 0; t < T; t += 2) {
-            float e1a, e1b, e2a, e2b;
-            if (INJECT) {
-                e1a = eps1[t]; e2a = eps2[t];
-                e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
-                e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
-            } else {
-                noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
-            }
-            {
-                const float u1 = sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
-                const float u2 = sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
-                sample_step<PROJ, false>(p, st, ter, sc, a, t, u1, u2, nod, 0);
-            }
-            if (t + 1 < T) {
-                const float u1 = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
-                const float u2 = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
-                sample_step<PROJ, false>(p, st, ter, sc, a, t + 1, u1, u2, nod, 0);
-            }
-        }
-        cost = sample_cost(p, sc, a, nullptr);
-        A.costs[(size_t)rover * K + k_local] = cost;
-        my_oob = (unsigned)a.oob;
-        if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }   // a NaN rollout gets zero weight
-    }
+    const uint32_t kg = A.k_begin + (uint32_t)(blockIdx.x * spb + k_in_block);
     if (my_oob) atomicAdd(&A.counters[rover * kCounterStride + 1], my_oob);
     if (my_nan) atomicAdd(&A.counters[rover * kCounterStride + 2], my_nan);
 
@@ -281,7 +232,7 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
     if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));   // critics_warp.py:346-347
     float s_b = w, s2_b = w * w;
     block_sum2(s_b, s2_b, s);
-    const int n_e = block_compact(w > 0.0f, tid, w, 0, s);
+    const int n_e = block_compact(w > 0.0f, k_in_block, w, 0, s);
     __syncthreads();
 
     const int stride = partial_stride(T);
@@ -297,7 +248,7 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
             if (active) {
                 const int t = 2 * pr;
                 for (int e = (G > 1) ? g : 0; e < n_e; e += G) {
-                    const int kl = blockIdx.x * B + s.list_i[e];
+                    const int kl = blockIdx.x * spb + s.list_i[e];
                     const float we = s.list_w[e];
                     float e1a, e1b, e2a, e2b;
                     if (INJECT) {
@@ -368,6 +319,276 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
         A.counters[rover * kCounterStride + 1] = 0u;
         A.counters[rover * kCounterStride + 2] = 0u;
     }
+}
+
+// ------------------------------------------------------------------ the fused kernel
+template <int PROJ, bool INJECT>
+__global__ void __launch_bounds__(kMaxBlock)
+mppi_fused_kernel(const __grid_constant__ FusedArgs A)
+{
+    extern __shared__ float smem_raw[];
+    const MppiParams& p = A.p;
+    const int T = p.T, K = p.K, B = blockDim.x, tid = threadIdx.x;
+    const int rover = blockIdx.y;
+    const Smem s = carve(smem_raw, T, B, A.nblocks);
+
+    const MppiState st = (A.states != nullptr) ? A.states[rover] : A.state;
+    const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
+    const Terr ter = make_terr(tr);
+    const SampleConsts sc = make_consts(p, st);
+    const NoiseKey nk = make_noise_key(A.seed, A.offset, (uint32_t)rover);
+
+    float* nominal1 = A.nominal1 + (size_t)rover * T;
+    float* nominal2 = A.nominal2 + (size_t)rover * T;
+    for (int t = tid; t < T; t += B) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
+    __syncthreads();
+
+    const int k_local = blockIdx.x * B + tid;
+    const bool valid = k_local < K;
+    const uint32_t kg = A.k_begin + (uint32_t)k_local;
+    const float* eps1 = INJECT ? A.noise + ((size_t)rover * 2 * K + k_local) * T : nullptr;
+    const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
+
+    // ---------------- phase 1: rollout + critics
+    float cost = CUDART_INF_F;
+    unsigned my_oob = 0, my_nan = 0;
+    if (valid) {
+        SampleAcc a;
+        sample_init<PROJ>(st, ter, a);
+        const DumpPtrs nod = {};
+        for (int t = 0; t < T; t += 2) {
+            float e1a, e1b, e2a, e2b;
+            if (INJECT) {
+                e1a = eps1[t]; e2a = eps2[t];
+                e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
+                e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
+            } else {
+                noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
+            }
+            {
+                const float u1 = sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
+                const float u2 = sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
+                sample_step<PROJ, false>(p, st, ter, sc, a, t, u1, u2, nod, 0);
+            }
+            if (t + 1 < T) {
+                const float u1 = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
+                const float u2 = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
+                sample_step<PROJ, false>(p, st, ter, sc, a, t + 1, u1, u2, nod, 0);
+            }
+        }
+        cost = sample_cost(p, sc, a, nullptr);
+        A.costs[(size_t)rover * K + k_local] = cost;
+        my_oob = (unsigned)a.oob;
+        if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }   // a NaN rollout gets zero weight
+    }
+    block_update<INJECT>(A, st, nk, s, rover, B, valid, tid, cost, my_oob, my_nan, nominal1, nominal2);
+}
+
+// ------------------------------------------------------------------ warp-specialised fused kernel (latency regime)
+// With K of a few thousand there is less than one warp of samples per SM and the step time is the latency of
+// ONE warp issuing ~560 mostly dependent instructions per horizon step (profiles/r1_ncu_fused_v1.md).  This
+// variant gives every group of 32 samples a CTA of four warps, one per SM sub-partition, and cuts the step along
+// its data dependences:
+//   warp 0  producer  Philox + Box-Muller -> u -> wheel filter -> (v, w); speed critic         [ring A]
+//   warp 1  chain     position / DEM corners / normal / tangent / Rodrigues: the only recurrence  [ring B]
+//   warp 2  wheels    wheel points + 2 DEM gathers + stride-2 slope critic
+//   warp 3  obstacle  costmap gather + lethal penalty, near-goal path critic, last point
+// Rings live in shared memory; stages are handed over with mbarriers (full/empty pairs), so the chain warp runs
+// its dependent chain without ever issuing the other roles' instructions.  Arithmetic per sample is unchanged
+// (same role functions as the monolithic kernel => same bits).
+constexpr int kPipeStages = 4;      // ring depth in chunks
+constexpr int kPipeChunk = 4;       // steps per chunk (even: noise comes in pairs of steps)
+constexpr int kPipeThreads = 128;
+
+struct PipeSmem {
+    unsigned long long full_a[kPipeStages], empty_a[kPipeStages], full_b[kPipeStages], empty_b[kPipeStages];
+    float ring_a[kPipeStages][kPipeChunk][2][32];     // v, w
+    float ring_b[kPipeStages][kPipeChunk][8][32];     // x, y, n.xyz, cur.xyz
+    float crit[6][32];                                // speed, slope, obs, pf_near, last_x, last_y
+    int oob[4][32];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok = 0;
+    for (unsigned spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > (1u << 22)) __trap();              // a broken pipeline must fail loudly, never hang the GPU
+    }
+}
+
+__host__ __device__ inline size_t pipe_smem_offset_floats(int T, int nblocks)
+{
+    return (smem_floats(T, kPipeThreads, nblocks) + 3) & ~(size_t)3;      // 16-byte aligned
+}
+
+template <int PROJ, bool INJECT>
+__global__ void __launch_bounds__(kPipeThreads)
+mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
+{
+    extern __shared__ __align__(16) float smem_raw[];
+    const MppiParams& p = A.p;
+    const int T = p.T, K = p.K, tid = threadIdx.x;
+    const int lane = tid & 31, role = tid >> 5;
+    const int rover = blockIdx.y;
+    const Smem s = carve(smem_raw, T, kPipeThreads, A.nblocks);
+    PipeSmem& ps = *reinterpret_cast<PipeSmem*>(smem_raw + pipe_smem_offset_floats(T, A.nblocks));
+
+    const MppiState st = (A.states != nullptr) ? A.states[rover] : A.state;
+    const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
+    const Terr ter = make_terr(tr);
+    const SampleConsts sc = make_consts(p, st);
+    const NoiseKey nk = make_noise_key(A.seed, A.offset, (uint32_t)rover);
+
+    float* nominal1 = A.nominal1 + (size_t)rover * T;
+    float* nominal2 = A.nominal2 + (size_t)rover * T;
+    for (int t = tid; t < T; t += kPipeThreads) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
+    if (tid == 0) {
+        for (int i = 0; i < kPipeStages; ++i) {
+            mbar_init(&ps.full_a[i], 32); mbar_init(&ps.empty_a[i], 32);
+            mbar_init(&ps.full_b[i], 32); mbar_init(&ps.empty_b[i], 64);
+        }
+    }
+    __syncthreads();
+
+    const int k_local = blockIdx.x * 32 + lane;
+    const bool valid = k_local < K;
+    const int k_read = valid ? k_local : K - 1;                 // idle lanes shadow the last sample (results unused)
+    const uint32_t kg = A.k_begin + (uint32_t)k_read;
+    const int nchunks = (T + kPipeChunk - 1) / kPipeChunk;
+    int oob = 0;
+
+    if (role == 0) {
+        // ---- producer: noise -> u -> wheel filter -> (v, w) ; speed critic
+        const float* eps1 = INJECT ? A.noise + ((size_t)rover * 2 * K + k_read) * T : nullptr;
+        const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
+        float wl = st.wheel_l, wr = st.wheel_r, speed = 0.0f;
+        for (int c = 0; c < nchunks; ++c) {
+            const int sg = c % kPipeStages;
+            mbar_wait(&ps.empty_a[sg], ((c / kPipeStages) & 1) ^ 1);
+#pragma unroll
+            for (int i = 0; i < kPipeChunk; i += 2) {
+                const int t = c * kPipeChunk + i;
+                if (t < T) {
+                    float e1a, e1b, e2a, e2b;
+                    if (INJECT) {
+                        e1a = eps1[t]; e2a = eps2[t];
+                        e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
+                        e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
+                    } else {
+                        noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
+                    }
+                    float v, w;
+                    role_filter(p, sc, wl, wr, sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max),
+                                sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max), v, w, speed);
+                    ps.ring_a[sg][i][0][lane] = v; ps.ring_a[sg][i][1][lane] = w;
+                    if (t + 1 < T) {
+                        role_filter(p, sc, wl, wr, sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max),
+                                    sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max), v, w, speed);
+                        ps.ring_a[sg][i + 1][0][lane] = v; ps.ring_a[sg][i + 1][1][lane] = w;
+                    }
+                }
+            }
+            mbar_arrive(&ps.full_a[sg]);
+        }
+        ps.crit[0][lane] = speed;
+    } else if (role == 1) {
+        // ---- chain: the recurrence
+        float x = st.x, y = st.y;
+        float3 prev = make_float3(st.hx, st.hy, st.hz), n;
+        if (PROJ == MPPI_PROJ_3D) {
+            int i0, j0;
+            const Quad q = corners(ter, x, y, i0, j0, oob);
+            prev = tangent(normal_on_grid(q, ter.res), prev);
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const int sg = c % kPipeStages;
+            const unsigned ph = (c / kPipeStages) & 1;
+            mbar_wait(&ps.full_a[sg], ph);
+            mbar_wait(&ps.empty_b[sg], ph ^ 1);
+#pragma unroll
+            for (int i = 0; i < kPipeChunk; ++i) {
+                const int t = c * kPipeChunk + i;
+                if (t < T) {
+                    const float v = ps.ring_a[sg][i][0][lane], w = ps.ring_a[sg][i][1][lane];
+                    role_chain<PROJ>(p, ter, x, y, prev, v, w, n, oob);
+                    float* o = &ps.ring_b[sg][i][0][lane];
+                    o[0] = x; o[32] = y; o[64] = n.x; o[96] = n.y; o[128] = n.z;
+                    o[160] = prev.x; o[192] = prev.y; o[224] = prev.z;
+                }
+            }
+            mbar_arrive(&ps.empty_a[sg]);
+            mbar_arrive(&ps.full_b[sg]);
+        }
+    } else if (role == 2) {
+        // ---- wheels + slope critic
+        float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e;
+        float slope = 0.0f;
+        for (int c = 0; c < nchunks; ++c) {
+            const int sg = c % kPipeStages;
+            mbar_wait(&ps.full_b[sg], (c / kPipeStages) & 1);
+#pragma unroll
+            for (int i = 0; i < kPipeChunk; i += 2) {                 // even steps only feed the critic
+                const int t = c * kPipeChunk + i;
+                if (t < T) {
+                    const float* o = &ps.ring_b[sg][i][0][lane];
+                    role_wheels<PROJ>(p, ter, t, o[0], o[32], make_float3(o[64], o[96], o[128]),
+                                      make_float3(o[160], o[192], o[224]), lw_e, rw_e, slope, oob);
+                }
+            }
+            mbar_arrive(&ps.empty_b[sg]);
+        }
+        ps.crit[1][lane] = slope;
+    } else {
+        // ---- obstacle + near-goal path critic + last point
+        float obs = 0.0f, pf_near = 0.0f, lx = st.x, ly = st.y;
+        for (int c = 0; c < nchunks; ++c) {
+            const int sg = c % kPipeStages;
+            mbar_wait(&ps.full_b[sg], (c / kPipeStages) & 1);
+#pragma unroll
+            for (int i = 0; i < kPipeChunk; ++i) {
+                const int t = c * kPipeChunk + i;
+                if (t < T) {
+                    lx = ps.ring_b[sg][i][0][lane]; ly = ps.ring_b[sg][i][1][lane];
+                    role_obstacle(p, st, ter, sc, t, lx, ly, pf_near, obs, oob);
+                }
+            }
+            mbar_arrive(&ps.empty_b[sg]);
+        }
+        ps.crit[2][lane] = obs; ps.crit[3][lane] = pf_near; ps.crit[4][lane] = lx; ps.crit[5][lane] = ly;
+    }
+    ps.oob[role][lane] = oob;
+    __syncthreads();
+
+    // ---- cost (critics_warp.py:325-329), owned by warp 0
+    float cost = CUDART_INF_F;
+    unsigned my_oob = 0, my_nan = 0;
+    const bool owner = (role == 0) && valid;
+    if (owner) {
+        SampleAcc a;
+        a.speed = ps.crit[0][lane]; a.slope = ps.crit[1][lane]; a.obs = ps.crit[2][lane];
+        a.pf_near = ps.crit[3][lane]; a.last_x = ps.crit[4][lane]; a.last_y = ps.crit[5][lane];
+        cost = sample_cost(p, sc, a, nullptr);
+        A.costs[(size_t)rover * K + k_local] = cost;
+        my_oob = (unsigned)(ps.oob[0][lane] + ps.oob[1][lane] + ps.oob[2][lane] + ps.oob[3][lane]);
+        if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }
+    }
+    block_update<INJECT>(A, st, nk, s, rover, 32, owner, lane, cost, my_oob, my_nan, nominal1, nominal2);
 }
 
 // ------------------------------------------------------------------ rank-partial combine (multi-GPU epilogue)
@@ -455,7 +676,7 @@ __global__ void mppi_sim_kernel(const __grid_constant__ SimArgs A)
     for (int t = 0; t < p.T; ++t) {
         update_position(x, y, prev, A.opt_v[t], p.dt);
         q = corners(ter, x, y, i, j, oob);
-        const float h = bilinear(x, y, q, ter.res);
+        const float h = bilinear(x, y, q, ter.rres);
         n = normal_on_grid(q, ter.res);
         prev = tangent(n, prev);
         const float3 cur = update_orientation(prev, A.opt_w[t], n, p.dt);
@@ -523,6 +744,31 @@ cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, 
         if (a.noise) MPPI_LAUNCH_FUSED(MPPI_PROJ_2D, true); else MPPI_LAUNCH_FUSED(MPPI_PROJ_2D, false);
     }
 #undef MPPI_LAUNCH_FUSED
+    return cudaGetLastError();
+}
+
+size_t pipe_smem_bytes(int T, int nblocks)
+{
+    return pipe_smem_offset_floats(T, nblocks) * sizeof(float) + sizeof(PipeSmem);
+}
+
+cudaError_t launch_fused_pipe(const FusedArgs& a, int proj, int n_rovers, cudaStream_t s)
+{
+    const dim3 grid(a.nblocks, n_rovers);
+    const size_t smem = pipe_smem_bytes(a.p.T, a.nblocks);
+    cudaError_t e;
+#define MPPI_LAUNCH_PIPE(PROJ, INJ)                                                    \
+    do {                                                                               \
+        e = ensure_smem(mppi_fused_pipe_kernel<PROJ, INJ>, smem);                      \
+        if (e != cudaSuccess) return e;                                                \
+        mppi_fused_pipe_kernel<PROJ, INJ><<<grid, kPipeThreads, smem, s>>>(a);         \
+    } while (0)
+    if (proj == MPPI_PROJ_3D) {
+        if (a.noise) MPPI_LAUNCH_PIPE(MPPI_PROJ_3D, true); else MPPI_LAUNCH_PIPE(MPPI_PROJ_3D, false);
+    } else {
+        if (a.noise) MPPI_LAUNCH_PIPE(MPPI_PROJ_2D, true); else MPPI_LAUNCH_PIPE(MPPI_PROJ_2D, false);
+    }
+#undef MPPI_LAUNCH_PIPE
     return cudaGetLastError();
 }
 

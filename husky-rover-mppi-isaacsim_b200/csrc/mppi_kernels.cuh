@@ -72,6 +72,7 @@ struct SimArgs {
 #define MPPI_DECLARE_LAUNCHERS(NS)                                                                              \
     namespace NS {                                                                                              \
     cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, cudaStream_t s);          \
+    cudaError_t launch_fused_pipe(const FusedArgs& a, int proj, int n_rovers, cudaStream_t s);                 \
     cudaError_t launch_combine(const CombineArgs& a, cudaStream_t s);                                          \
     cudaError_t launch_dump(const DumpArgs& a, int proj, cudaStream_t s);                                      \
     cudaError_t launch_weights(const float* costs, int K, float lambda, float* weights, cudaStream_t s);      \

@@ -41,12 +41,18 @@ enum { MPPI_PROJ_2D = 2, MPPI_PROJ_3D = 3 };   /* MPPI_step(proj="2d"|"3d")  MPP
  *          oracle within tolerance, not bit-for-bit). */
 enum { MPPI_MATH_STRICT = 0, MPPI_MATH_FAST = 1 };
 
+/* Fused-kernel variant.  Both compute the same bits; they differ in how a sample's step is mapped to warps.
+ *  MONO: one thread per sample does everything (throughput regime, large K).
+ *  PIPE: four specialised warps per 32 samples (noise/filter -> dependent chain -> wheel/slope and obstacle
+ *        critics) handing stages over through shared-memory rings (latency regime, K of a few thousand). */
+enum { MPPI_VARIANT_AUTO = 0, MPPI_VARIANT_MONO = 1, MPPI_VARIANT_PIPE = 2 };
+
 /* Every tunable / literal of the reference hot path. Defaults via mppi_default_params. */
 typedef struct MppiParams {
     int32_t K;              /* number_of_trajectories                       config.yaml:7   */
     int32_t T;              /* number_of_iterations (horizon steps), 2..512  config.yaml:5   */
     int32_t math;           /* MPPI_MATH_*                                                   */
-    int32_t reserved0;
+    int32_t variant;        /* MPPI_VARIANT_*: which fused kernel runs the step (0 = choose by K)             */
     float dt;               /* config.yaml:6 */
     float u1_min, u1_max, u2_min, u2_max;       /* config.yaml:21-24 */
     float v_min, v_max, w_min, w_max;           /* config.yaml:11-12,15-16 */

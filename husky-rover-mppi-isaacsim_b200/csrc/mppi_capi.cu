@@ -382,3 +382,20 @@ extern "C" int mppi_test_noise(uint64_t seed, uint64_t offset, uint32_t rover, u
     if (e != cudaSuccess) return cuda_fail(e, "launch_noise");
     return MPPI_OK;
 }
+
+extern "C" int mppi_test_normalize(const float* v_dev, float* out_dev, float* ref_dev, int32_t n, void* stream)
+{
+    if (!v_dev || !out_dev || !ref_dev || n < 1) return MPPI_ERR_INVALID_ARG;
+    cudaError_t e = strict::launch_normalize_test(v_dev, out_dev, ref_dev, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_normalize_test");
+    return MPPI_OK;
+}
+
+extern "C" int mppi_test_divsqrt(const float* a_dev, const float* b_dev, float* out_dev, float* ref_dev, int32_t n,
+                                 void* stream)
+{
+    if (!a_dev || !b_dev || !out_dev || !ref_dev || n < 1) return MPPI_ERR_INVALID_ARG;
+    cudaError_t e = strict::launch_divsqrt_test(a_dev, b_dev, out_dev, ref_dev, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_divsqrt_test");
+    return MPPI_OK;
+}

@@ -387,25 +387,31 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
 // ------------------------------------------------------------------ warp-specialised fused kernel (latency regime)
 // With K of a few thousand there is less than one warp of samples per SM and the step time is the latency of
 // ONE warp issuing ~560 mostly dependent instructions per horizon step (profiles/r1_ncu_fused_v1.md).  This
-// variant gives every group of 32 samples a CTA of four warps, one per SM sub-partition, and cuts the step along
-// its data dependences:
-//   warp 0  producer  Philox + Box-Muller -> u -> wheel filter -> (v, w); speed critic         [ring A]
-//   warp 1  chain     position / DEM corners / normal / tangent / Rodrigues: the only recurrence  [ring B]
-//   warp 2  wheels    wheel points + 2 DEM gathers + stride-2 slope critic
-//   warp 3  obstacle  costmap gather + lethal penalty, near-goal path critic, last point
-// Rings live in shared memory; stages are handed over with mbarriers (full/empty pairs), so the chain warp runs
-// its dependent chain without ever issuing the other roles' instructions.  Arithmetic per sample is unchanged
-// (same role functions as the monolithic kernel => same bits).
+// variant gives every group of 32 samples a CTA of six warps and cuts the step along its data dependences:
+//   warps 0,1  noise     Philox + Box-Muller -> u (alternate chunks; the stream is counter-based)   [ring U]
+//   warp  4    filter    wheel filter u -> (v, w); speed critic                                     [ring A]
+//   warp  2    chain     position / DEM corners / normal / tangent / Rodrigues: the only recurrence  [ring B]
+//   warp  3    wheels    wheel points + 2 DEM gathers + stride-2 slope critic
+//   warp  5    obstacle  costmap gather + lethal penalty, near-goal path critic, last point
+// Warp w runs on SM sub-partition w % 4, so the chain and the wheel warps own a scheduler each and the light
+// roles share the other two.  Rings live in shared memory; chunks of kPipeChunk steps are handed over with
+// mbarriers (full/empty pairs), so the chain warp runs its dependent chain without ever issuing the other
+// roles' instructions.  Arithmetic per sample is unchanged (same device functions => same bits).
 constexpr int kPipeStages = 4;      // ring depth in chunks
 constexpr int kPipeChunk = 4;       // steps per chunk (even: noise comes in pairs of steps)
-constexpr int kPipeThreads = 128;
+constexpr int kNoiseWarps = 2;
+constexpr int kPipeThreads = 192;
+enum { ROLE_NOISE0 = 0, ROLE_NOISE1 = 1, ROLE_CHAIN = 2, ROLE_WHEELS = 3, ROLE_FILTER = 4, ROLE_OBST = 5 };
 
 struct PipeSmem {
-    unsigned long long full_a[kPipeStages], empty_a[kPipeStages], full_b[kPipeStages], empty_b[kPipeStages];
-    float ring_a[kPipeStages][kPipeChunk][2][32];     // v, w
+    unsigned long long full_u[kPipeStages], empty_u[kPipeStages];
+    unsigned long long full_a[kPipeStages], empty_a[kPipeStages];
+    unsigned long long full_b[kPipeStages], empty_b[kPipeStages];
+    float ring_u[kPipeStages][kPipeChunk][2][32];     // u1, u2
+    float ring_a[kPipeStages][kPipeChunk][3][32];     // v, sin(w dt), cos(w dt)
     float ring_b[kPipeStages][kPipeChunk][8][32];     // x, y, n.xyz, cur.xyz
     float crit[6][32];                                // speed, slope, obs, pf_near, last_x, last_y
-    int oob[4][32];
+    int oob[6][32];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -460,6 +466,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     for (int t = tid; t < T; t += kPipeThreads) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
     if (tid == 0) {
         for (int i = 0; i < kPipeStages; ++i) {
+            mbar_init(&ps.full_u[i], 32); mbar_init(&ps.empty_u[i], 32);
             mbar_init(&ps.full_a[i], 32); mbar_init(&ps.empty_a[i], 32);
             mbar_init(&ps.full_b[i], 32); mbar_init(&ps.empty_b[i], 64);
         }
@@ -473,14 +480,13 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     const int nchunks = (T + kPipeChunk - 1) / kPipeChunk;
     int oob = 0;
 
-    if (role == 0) {
-        // ---- producer: noise -> u -> wheel filter -> (v, w) ; speed critic
+    if (role < kNoiseWarps) {
+        // ---- noise: eps -> u for chunks c = role, role + kNoiseWarps, ...
         const float* eps1 = INJECT ? A.noise + ((size_t)rover * 2 * K + k_read) * T : nullptr;
         const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
-        float wl = st.wheel_l, wr = st.wheel_r, speed = 0.0f;
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = role; c < nchunks; c += kNoiseWarps) {
             const int sg = c % kPipeStages;
-            mbar_wait(&ps.empty_a[sg], ((c / kPipeStages) & 1) ^ 1);
+            mbar_wait(&ps.empty_u[sg], ((c / kPipeStages) & 1) ^ 1);
 #pragma unroll
             for (int i = 0; i < kPipeChunk; i += 2) {
                 const int t = c * kPipeChunk + i;
@@ -493,21 +499,38 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                     } else {
                         noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
                     }
-                    float v, w;
-                    role_filter(p, sc, wl, wr, sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max),
-                                sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max), v, w, speed);
-                    ps.ring_a[sg][i][0][lane] = v; ps.ring_a[sg][i][1][lane] = w;
+                    ps.ring_u[sg][i][0][lane] = sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
+                    ps.ring_u[sg][i][1][lane] = sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
                     if (t + 1 < T) {
-                        role_filter(p, sc, wl, wr, sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max),
-                                    sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max), v, w, speed);
-                        ps.ring_a[sg][i + 1][0][lane] = v; ps.ring_a[sg][i + 1][1][lane] = w;
+                        ps.ring_u[sg][i + 1][0][lane] = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
+                        ps.ring_u[sg][i + 1][1][lane] = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
                     }
                 }
             }
+            mbar_arrive(&ps.full_u[sg]);
+        }
+    } else if (role == ROLE_FILTER) {
+        // ---- wheel filter u -> (v, w) (sequential in t) + speed critic
+        float wl = st.wheel_l, wr = st.wheel_r, speed = 0.0f;
+        for (int c = 0; c < nchunks; ++c) {
+            const int sg = c % kPipeStages;
+            const unsigned ph = (c / kPipeStages) & 1;
+            mbar_wait(&ps.full_u[sg], ph);
+            mbar_wait(&ps.empty_a[sg], ph ^ 1);
+#pragma unroll
+            for (int i = 0; i < kPipeChunk; ++i) {
+                const int t = c * kPipeChunk + i;
+                if (t < T) {
+                    float v, sn, cs;
+                    role_filter(p, sc, wl, wr, ps.ring_u[sg][i][0][lane], ps.ring_u[sg][i][1][lane], v, sn, cs, speed);
+                    ps.ring_a[sg][i][0][lane] = v; ps.ring_a[sg][i][1][lane] = sn; ps.ring_a[sg][i][2][lane] = cs;
+                }
+            }
+            mbar_arrive(&ps.empty_u[sg]);
             mbar_arrive(&ps.full_a[sg]);
         }
         ps.crit[0][lane] = speed;
-    } else if (role == 1) {
+    } else if (role == ROLE_CHAIN) {
         // ---- chain: the recurrence
         float x = st.x, y = st.y;
         float3 prev = make_float3(st.hx, st.hy, st.hz), n;
@@ -525,17 +548,21 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             for (int i = 0; i < kPipeChunk; ++i) {
                 const int t = c * kPipeChunk + i;
                 if (t < T) {
-                    const float v = ps.ring_a[sg][i][0][lane], w = ps.ring_a[sg][i][1][lane];
-                    role_chain<PROJ>(p, ter, x, y, prev, v, w, n, oob);
+                    const float v = ps.ring_a[sg][i][0][lane];
+                    const float sn = ps.ring_a[sg][i][1][lane], cs = ps.ring_a[sg][i][2][lane];
+                    role_chain<PROJ>(p, ter, x, y, prev, v, sn, cs, n, oob);
                     float* o = &ps.ring_b[sg][i][0][lane];
-                    o[0] = x; o[32] = y; o[64] = n.x; o[96] = n.y; o[128] = n.z;
-                    o[160] = prev.x; o[192] = prev.y; o[224] = prev.z;
+                    o[0] = x; o[32] = y;
+                    if ((i & 1) == 0) {                  // only even steps feed the wheel / slope role
+                        o[64] = n.x; o[96] = n.y; o[128] = n.z;
+                        o[160] = prev.x; o[192] = prev.y; o[224] = prev.z;
+                    }
                 }
             }
             mbar_arrive(&ps.empty_a[sg]);
             mbar_arrive(&ps.full_b[sg]);
         }
-    } else if (role == 2) {
+    } else if (role == ROLE_WHEELS) {
         // ---- wheels + slope critic
         float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e;
         float slope = 0.0f;
@@ -585,7 +612,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         a.pf_near = ps.crit[3][lane]; a.last_x = ps.crit[4][lane]; a.last_y = ps.crit[5][lane];
         cost = sample_cost(p, sc, a, nullptr);
         A.costs[(size_t)rover * K + k_local] = cost;
-        my_oob = (unsigned)(ps.oob[0][lane] + ps.oob[1][lane] + ps.oob[2][lane] + ps.oob[3][lane]);
+        for (int r = 0; r < 6; ++r) my_oob += (unsigned)ps.oob[r][lane];
         if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }
     }
     block_update<INJECT>(A, st, nk, s, rover, 32, owner, lane, cost, my_oob, my_nan, nominal1, nominal2);
@@ -674,12 +701,12 @@ __global__ void mppi_sim_kernel(const __grid_constant__ SimArgs A)
     float3 n = normal_on_grid(q, ter.res);
     float3 prev = tangent(n, make_float3(A.state.hx, A.state.hy, A.state.hz));
     for (int t = 0; t < p.T; ++t) {
-        update_position(x, y, prev, A.opt_v[t], p.dt);
+        update_position(x, y, prev, A.opt_v[t], p.dt, oob);
         q = corners(ter, x, y, i, j, oob);
         const float h = bilinear(x, y, q, ter.rres);
         n = normal_on_grid(q, ter.res);
         prev = tangent(n, prev);
-        const float3 cur = update_orientation(prev, A.opt_w[t], n, p.dt);
+        const float3 cur = update_orientation(prev, A.opt_w[t], n, p.dt, oob);
         A.sim_traj[3 * t] = x; A.sim_traj[3 * t + 1] = y; A.sim_traj[3 * t + 2] = h;
         A.sim_heading[3 * t] = cur.x; A.sim_heading[3 * t + 1] = cur.y; A.sim_heading[3 * t + 2] = cur.z;
         prev = cur;
@@ -700,6 +727,29 @@ __global__ void mppi_detmath_kernel(int fn, const float* x, float* y0, float* y1
     }
     y0[i] = a;
     if (y1) y1[i] = b;
+}
+
+// product normalize3 / fdiv / fsqrt against the IEEE intrinsics (only meaningful in the STRICT flavour)
+__global__ void mppi_normalize_test_kernel(const float* v, float* out, float* ref, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 a = make_float3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    const float3 r = normalize3_maybe_unit(a);
+    out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    const float s = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)), __fmul_rn(a.z, a.z)));
+    ref[3 * i] = __fdiv_rn(a.x, s); ref[3 * i + 1] = __fdiv_rn(a.y, s); ref[3 * i + 2] = __fdiv_rn(a.z, s);
+}
+
+// scalar fdiv(a, b) and fsqrt(|a|) against the IEEE intrinsics
+__global__ void mppi_divsqrt_test_kernel(const float* a, const float* b, float* out, float* ref, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[2 * i] = fdiv(a[i], b[i]);
+    ref[2 * i] = __fdiv_rn(a[i], b[i]);
+    out[2 * i + 1] = fsqrt(fabsf(a[i]));
+    ref[2 * i + 1] = __fsqrt_rn(fabsf(a[i]));
 }
 
 __global__ void mppi_noise_kernel(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k_begin, int K, int T,
@@ -810,6 +860,18 @@ cudaError_t launch_sim(const SimArgs& a, cudaStream_t s)
 cudaError_t launch_detmath(int fn, const float* x, float* y0, float* y1, int n, cudaStream_t s)
 {
     mppi_detmath_kernel<<<(n + 255) / 256, 256, 0, s>>>(fn, x, y0, y1, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_normalize_test(const float* v, float* out, float* ref, int n, cudaStream_t s)
+{
+    mppi_normalize_test_kernel<<<(n + 255) / 256, 256, 0, s>>>(v, out, ref, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_divsqrt_test(const float* a, const float* b, float* out, float* ref, int n, cudaStream_t s)
+{
+    mppi_divsqrt_test_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, out, ref, n);
     return cudaGetLastError();
 }
 

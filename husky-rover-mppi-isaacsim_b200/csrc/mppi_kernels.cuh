@@ -80,6 +80,8 @@ struct SimArgs {
     cudaError_t launch_detmath(int fn, const float* x, float* y0, float* y1, int n, cudaStream_t s);          \
     cudaError_t launch_noise(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k_begin, int K, int T,  \
                              float* e1, float* e2, cudaStream_t s);                                            \
+    cudaError_t launch_normalize_test(const float* v, float* out, float* ref, int n, cudaStream_t s);         \
+    cudaError_t launch_divsqrt_test(const float* a, const float* b, float* out, float* ref, int n, cudaStream_t s); \
     size_t fused_smem_bytes(int T, int block, int nblocks);                                                    \
     }
 

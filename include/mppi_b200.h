@@ -194,6 +194,12 @@ int mppi_test_detmath(int32_t fn, const float *x_dev, float *y0_dev, float *y1_d
 int mppi_test_noise(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k_begin, int32_t K, int32_t T,
                     int32_t math, float *eps1_dev, float *eps2_dev, void *stream);
 
+/* Test hooks: the STRICT flavour's branch-free normalize3 / fdiv / fsqrt next to the IEEE intrinsics
+ * (__fsqrt_rn, __fdiv_rn).  v_dev [3n] -> out_dev / ref_dev [3n];  a_dev, b_dev [n] -> out_dev / ref_dev [2n]
+ * = {a/b, sqrt|a|}. */
+int mppi_test_normalize(const float *v_dev, float *out_dev, float *ref_dev, int32_t n, void *stream);
+int mppi_test_divsqrt(const float *a_dev, const float *b_dev, float *out_dev, float *ref_dev, int32_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

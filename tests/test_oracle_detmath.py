@@ -73,3 +73,17 @@ def test_philox_normals_statistics_and_replay(oracle):
     # libm Box-Muller agrees with the det one to rounding
     l1, _ = oracle.philox_normals(42, 3, 512, 100, math=oracle.MATH_LIBM)
     assert np.max(np.abs(l1 - e1[:512])) < 5e-6
+
+
+def test_near_unit_normalisation_shortcut_is_ieee_exact(tmp_path):
+    """The STRICT kernels skip both MUFU ops when re-normalising an almost-unit vector (csrc/mppi_device.cuh,
+    normalize3).  tests/arith_near_unit.c proves by exhaustive enumeration that the shortcut equals IEEE sqrt and
+    division for every squared norm in the window, every resulting divisor and every numerator mantissa."""
+    import os
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "arith_near_unit.c")
+    exe = str(tmp_path / "arith_near_unit")
+    subprocess.run(["/usr/bin/gcc", "-O2", "-ffp-contract=off", "-mfma", src, "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    bad_s, bad_q, n = (int(x) for x in r.stdout.split())
+    assert r.returncode == 0 and bad_s == 0 and bad_q == 0 and n > 3e9

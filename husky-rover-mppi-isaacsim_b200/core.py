@@ -34,10 +34,11 @@ class Core:
         p.math = capi.MATH_STRICT if math == "strict" else capi.MATH_FAST
         for k, v in overrides.items():
             setattr(p, "lam" if k in ("lambda_", "temperature") else k, v)
+        # horizon = dt * v_max * T is formed in double on the host (MPPI_isaac.py:440), then cast to fp32
         if params is None and "horizon" not in overrides:
-            p.horizon = p.dt * p.v_max * T
+            p.horizon = overrides.get("dt", 0.045) * overrides.get("v_max", 2.0) * T
         if params is None and "target_speed" not in overrides:
-            p.target_speed = p.v_max
+            p.target_speed = overrides.get("v_max", 2.0)
         self.p, self.K, self.T = p, K, T
         self.device = torch.device("cuda", device)
         self.max_rovers = max_rovers

@@ -1,0 +1,218 @@
+"""GPU: the other operating modes of the core, each against the oracle --
+sample-sharded partial/combine (ranks emulated on one GPU), multi-rover batches, the reference-shaped
+`MPPI_Controller` facade (drop-in surface), validation/visualiser dumps."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import default_state, terrain
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def close(a, b, floor=1e-3):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def make_core(K, T, name="C1", **kw):
+    import torch
+    from mppi_b200.core import Core
+    dem, cm, hw = terrain(name)
+    core = Core(K, T, **kw)
+    core.set_terrain(torch.from_numpy(dem).cuda(), hw, torch.from_numpy(cm).cuda())
+    return core, dem, cm, hw
+
+
+def state_struct(st):
+    from mppi_b200 import capi
+    s = capi.MppiState()
+    for k, v in st.items():
+        setattr(s, k, float(v))
+    return s
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+@pytest.mark.parametrize("lam", [0.3, 2000.0])
+def test_sample_sharded_partials_fold_to_the_unsharded_update(oracle, G, lam):
+    """G ranks each roll out K/G samples keyed by GLOBAL sample id, publish their softmax
+    partial, and the rank-ordered combine reproduces the single-GPU update (argmin exactly, nominal <= 1e-6 rel).
+    Ranks are emulated as G sequential launches on one GPU -- the all-gather itself is covered by the gloo test."""
+    import torch
+    K, T = 4096, 60
+    st = default_state()
+    ref_eps = oracle.philox_normals(5, 11, K, T)
+    dem, cm, hw = terrain("C1")
+    nom = np.full(T, 0.35, np.float32)
+    ref = oracle.mppi_step(oracle.make_params(K=K, T=T, lam=lam), dem, hw, cm, st, nom, nom, ref_eps[0], ref_eps[1],
+                           dump=["cost"])
+    core, *_ = make_core(K // G, T, lambda_=lam)
+    s = state_struct(st)
+    parts = torch.zeros((G, core.partial_floats()), device="cuda")
+    costs = []
+    for g in range(G):
+        core.set_nominal(nom, nom)
+        core.step_partial(s, parts[g], k_begin=g * (K // G), seed=5, offset=11)
+        torch.cuda.synchronize()
+        costs.append(core.costs[0].cpu().numpy().copy())
+    assert np.array_equal(np.concatenate(costs), ref.dump["cost"])          # costs independent of the sharding
+    core.set_nominal(nom, nom)
+    core.combine_partials(s, parts, G)
+    torch.cuda.synchronize()
+    got = core.read_stats()
+    assert got["argmin"] == ref.argmin and got["min_cost"] == ref.min_cost
+    assert close(core.optimal_u1[0].cpu().numpy(), ref.nominal1_f64) < 1e-5
+    assert close(core.optimal_u2[0].cpu().numpy(), ref.nominal2_f64) < 1e-5
+    assert close(got["weights_sum"], ref.weights_sum) < 1e-5
+    # the GPU partial layout is what the oracle's combine expects: fold it on the CPU too
+    p = parts.cpu().numpy()
+    n1, n2, m, arg, S = oracle.combine_partials(np.concatenate([p[:, :3], p[:, 4:]], axis=1), T, lam)
+    assert arg == ref.argmin and close(n1, ref.nominal1_f64) < 1e-5
+    core.close()
+
+
+def test_unsharded_and_sharded_agree_on_the_device(oracle):
+    """Same controller, once with mppi_step and once with step_partial + combine (G = 1): identical outputs."""
+    import torch
+    K, T = 2048, 50
+    st = state_struct(default_state())
+    core, *_ = make_core(K, T, lambda_=50.0)
+    core.step(st, seed=3, offset=9)
+    torch.cuda.synchronize()
+    a = (core.optimal_u1.cpu().numpy().copy(), core.optimal_v.cpu().numpy().copy(), core.read_stats())
+    core.set_nominal(np.zeros(T, np.float32), np.zeros(T, np.float32))
+    part = torch.zeros(core.partial_floats(), device="cuda")
+    core.step_partial(st, part, k_begin=0, seed=3, offset=9)
+    core.combine_partials(st, part, 1)
+    torch.cuda.synchronize()
+    b = (core.optimal_u1.cpu().numpy(), core.optimal_v.cpu().numpy(), core.read_stats())
+    assert a[2]["argmin"] == b[2]["argmin"]
+    assert close(b[0], a[0]) < 1e-6 and close(b[1], a[1]) < 1e-6
+    core.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["mono", "pipe"])
+def test_multi_rover_batch_matches_per_rover_oracle(oracle, variant):
+    """BASELINE config 4 in small: R independent rovers, own map / pose / goal / nominal each, one launch."""
+    import torch
+    from mppi_b200.core import Core
+    from mppi_b200 import synthetic as syn
+    R, K, T = 6, 256, 40
+    hw, gs, cms = 12.8, 256, 128
+    rng = np.random.default_rng(7)
+    dems, cms_, states, noms = [], [], [], []
+    for r in range(R):
+        bumps = [((float(rng.uniform(-8, 8)), float(rng.uniform(-8, 8))), float(rng.uniform(0.5, 2.0)),
+                  float(rng.uniform(1.0, 3.0))) for _ in range(5)]
+        dems.append(syn.crater_dem(gs, hw, bumps=bumps).numpy())
+        cms_.append(syn.rock_costmap(cms, hw, n_rocks=40, seed=100 + r))
+        th = rng.uniform(0, 2 * np.pi)
+        states.append(default_state(x=float(rng.uniform(-5, 5)), y=float(rng.uniform(-5, 5)), hx=float(np.cos(th)),
+                                    hy=float(np.sin(th)), goal_x=float(rng.uniform(-9, 9)),
+                                    goal_y=float(rng.uniform(-9, 9)), wheel_l=float(rng.uniform(0, 1)),
+                                    wheel_r=float(rng.uniform(0, 1))))
+        noms.append((rng.uniform(-0.5, 1, T).astype(np.float32), rng.uniform(-0.5, 1, T).astype(np.float32)))
+    core = Core(K, T, max_rovers=R, variant=variant)
+    core.set_terrain_batched(torch.from_numpy(np.stack(dems)).cuda(), hw, torch.from_numpy(np.stack(cms_)).cuda())
+    core.set_nominal(np.stack([n[0] for n in noms]), np.stack([n[1] for n in noms]), n_rovers=R)
+    sdev = Core.pack_states([state_struct(s) for s in states], core.device)
+    core.step_batched(sdev, R, seed=21, offset=4)
+    torch.cuda.synchronize()
+    for r in range(R):
+        e1, e2 = oracle.philox_normals(21, 4, K, T, rover=r)
+        ref = oracle.mppi_step(oracle.make_params(K=K, T=T), dems[r], hw, cms_[r], states[r], noms[r][0], noms[r][1],
+                               e1, e2, dump=["cost"])
+        st = core.read_stats(r)
+        assert np.array_equal(core.costs[r].cpu().numpy(), ref.dump["cost"]), r
+        assert st["argmin"] == ref.argmin and st["oob"] == ref.oob_clamps == 0
+        assert close(core.optimal_u1[r].cpu().numpy(), ref.nominal1) < RTOL
+        assert close(core.optimal_v[r].cpu().numpy(), ref.opt_v) < RTOL
+    core.close()
+
+
+def test_controller_facade_is_a_drop_in(oracle):
+    """The reference driver's call sequence (visual_terrain_stack_full_terrain.py:449-515) against the facade:
+    Surface / Robot / MPPI_Controller construction, warp_setup, reset, MPPI_step, `.numpy()[0]` reads, attribute
+    writes between steps, costmap assign, Z_wp swap, sim rollout reads -- and the numbers equal the oracle's."""
+    import torch
+    import mppi_b200
+    from mppi_b200 import MPPI_Controller, Robot, Surface
+    dem, cm, hw = terrain("C1")
+    surface = Surface("", "", "", "", grid_size=1500, half_width=75.0, origin=(0, 0), bumps=[], radius_robot=0.3)
+    surface.Z = dem
+    surface.costmap_size, surface.costmap_resolution, surface.costmap = 750, 150.0 / 750, cm
+    robot = Robot(x=-60.57, y=-60.23, heading_vector=[1.0, 0.0, 0.0], config_file=mppi_b200.DEFAULT_CONFIG)
+    ctl = MPPI_Controller(surface, robot, mppi_b200.DEFAULT_CONFIG, goal_x=65.8, goal_y=65.4, goal_orientation=2.2,
+                          seed=77)
+    ctl.warp_setup()
+    K, T = ctl.number_of_trajectories, ctl.number_of_iterations
+    assert (K, T) == (1000, 100)
+    n1 = np.zeros(T, np.float32)
+    n2 = np.zeros(T, np.float32)
+    st = default_state()
+    p = oracle.make_params(K=K, T=T)
+    for it in range(3):
+        ctl.reset("controller")
+        ctl.MPPI_step(proj="3d")
+        lin = ctl.optimal_lin_vel_wp.numpy()[0]
+        ang = ctl.optimal_ang_vel_wp.numpy()[0]
+        e1, e2 = oracle.philox_normals(77, it, K, T)
+        ref = oracle.mppi_step(p, dem, hw, cm, st, n1, n2, e1, e2, dump=["cost"])
+        assert np.array_equal(ctl.costs_wp.numpy(), ref.dump["cost"])
+        assert close([lin, ang], [ref.opt_v[0], ref.opt_w[0]]) < RTOL
+        assert close(ctl.optimal_u1_wp.numpy(), ref.nominal1) < RTOL
+        assert close(ctl.trajectories_sim.numpy(), ref.sim_traj, floor=1.0) < RTOL     # lazy launch 9
+        assert close(ctl.heading_vectors_sim.numpy(), ref.sim_heading, floor=1.0) < RTOL
+        assert ctl.stats()["argmin"] == ref.argmin
+        # what the driver mutates between steps
+        n1, n2 = ctl.optimal_u1_wp.numpy().copy(), ctl.optimal_u2_wp.numpy().copy()
+        t0, h0 = ref.sim_traj[0], ref.sim_heading[0]
+        robot.update_position(float(t0[0]), float(t0[1]), float(t0[2]), h0.astype(np.float64))
+        ctl.std_dev_u1 = max(0.25, 0.25 - float(ang) ** 2 / 3)
+        ctl.std_dev_u2 = max(0.25, 0.25 + float(ang) ** 2 / 3)
+        robot.left_wheel_speed = float(lin) - float(ang) * robot.radius / 2
+        robot.right_wheel_speed = float(lin) + float(ang) * robot.radius / 2
+        hv = h0.astype(np.float64) / np.linalg.norm(h0.astype(np.float64))
+        st = default_state(x=float(t0[0]), y=float(t0[1]), hx=hv[0], hy=hv[1], hz=hv[2],
+                           wheel_l=robot.left_wheel_speed, wheel_r=robot.right_wheel_speed,
+                           sigma1=ctl.std_dev_u1, sigma2=ctl.std_dev_u2)
+    # K x T trajectories only on request (visualiser path)
+    tr = ctl.trajectories.numpy()
+    assert tr.shape == (K * T, 3)
+    # block change: new costmap through assign(), DEM re-pointed zero-copy at another device array, goal moved
+    cm2 = np.ascontiguousarray(cm[::-1]).copy()
+    ctl.surface.costmap = cm2
+    ctl.costmap_wp.assign(cm2.flatten())
+    dem2 = torch.from_numpy(np.ascontiguousarray(dem.T)).cuda()
+    ctl.Z_wp = dem2
+    ctl.goal_x -= 3.0
+    ctl.goal_y += 2.0
+    ctl.MPPI_step(proj="3d")
+    e1, e2 = oracle.philox_normals(77, 3, K, T)
+    st["goal_x"], st["goal_y"] = ctl.goal_x, ctl.goal_y
+    ref = oracle.mppi_step(p, np.ascontiguousarray(dem.T), hw, cm2, st, n1, n2, e1, e2, dump=["cost"])
+    assert np.array_equal(ctl.costs_wp.numpy(), ref.dump["cost"])
+    v, w = ctl.step_command("2d")                        # one-call variant, 2-D projection
+    assert 0.0 <= v <= 2.0 and -1.0 <= w <= 1.0
+    ctl.close()
+
+
+def test_controller_run_closed_loop_reaches_a_near_goal():
+    """MPPI_Controller.run (MPPI_isaac.py:755-805): the controller's own model as the plant, short hop."""
+    import mppi_b200
+    from mppi_b200 import MPPI_Controller, Robot, Surface
+    dem, cm, hw = terrain("small")
+    surface = Surface("", "", "", "", grid_size=256, half_width=12.8, origin=(0, 0), bumps=[], radius_robot=0.3)
+    surface.Z = dem
+    surface.costmap_size, surface.costmap_resolution, surface.costmap = 128, 25.6 / 128, np.zeros_like(cm)
+    robot = Robot(x=-6.0, y=-6.0, heading_vector=[1.0, 1.0, 0.0], config_file=mppi_b200.DEFAULT_CONFIG)
+    ctl = MPPI_Controller(surface, robot, mppi_b200.DEFAULT_CONFIG, goal_x=-3.0, goal_y=-3.0, goal_orientation=0.0,
+                          overrides=dict(number_of_trajectories=2048, number_of_iterations=60))
+    loops = ctl.run("3d", max_loops=400)
+    d0 = np.hypot(-6.0 + 3.0, -6.0 + 3.0)
+    d1 = np.hypot(robot.x[-1] + 3.0, robot.y[-1] + 3.0)
+    assert loops > 5 and d1 < 0.75 * d0, (loops, d0, d1)          # it moves toward the goal
+    assert len(robot.x) == loops + 1 and len(robot.lin_vel) == loops
+    ctl.close()

@@ -49,10 +49,11 @@ class GpuCore:
         p.math = capi.MATH_STRICT if math == "strict" else capi.MATH_FAST
         for k, v in param_overrides.items():
             setattr(p, "lam" if k == "lambda_" else k, v)
+        # horizon = dt * v_max * T is formed in DOUBLE on the host (MPPI_isaac.py:440) and only then cast to fp32
         if "horizon" not in param_overrides:
-            p.horizon = p.dt * p.v_max * T
+            p.horizon = param_overrides.get("dt", 0.045) * param_overrides.get("v_max", 2.0) * T
         if "target_speed" not in param_overrides:
-            p.target_speed = p.v_max
+            p.target_speed = param_overrides.get("v_max", 2.0)
         self.p = p
         self.h = C.c_void_p()
         capi.check(self.L.mppi_create(C.byref(p), 0, max_rovers, C.byref(self.h)), "create")

@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--K", type=int, default=0, help="override the workload's samples per GPU (diagnostics)")
+    ap.add_argument("--T", type=int, default=0, help="override the workload's horizon (diagnostics)")
     return ap.parse_args()
 
 
@@ -54,9 +56,13 @@ def peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
 
 
-def build_workload(name):
+def build_workload(name, K_override=0, T_override=0):
     from mppi_b200 import synthetic as syn
     w = syn.WORKLOADS[name]
+    if K_override or T_override:
+        import dataclasses
+        w = dataclasses.replace(w, K=K_override or w.K, T=T_override or w.T,
+                                name=f"{w.name} [override K={K_override or w.K} T={T_override or w.T}]")
     dem = syn.crater_dem(w.grid_size, w.half_width).numpy()
     cm = syn.rock_costmap(w.costmap_size, w.half_width)
     start, goal = syn.workload_start_goal(w)
@@ -99,7 +105,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, dem, cm, start, goal = build_workload(args.workload)
+    w, dem, cm, start, goal = build_workload(args.workload, args.K, args.T)
     base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "MPPI sample-steps/s", "value": base["value"], "unit": "sample-steps/s",
@@ -185,7 +191,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
-    w, dem_np, cm_np, start, goal = build_workload(args.workload)
+    w, dem_np, cm_np, start, goal = build_workload(args.workload, args.K, args.T)
     K, T = w.K, w.T                       # per-GPU samples
     K_total = K * n_gpus
     core = Core(K, T, device=local_rank, math=args.math,

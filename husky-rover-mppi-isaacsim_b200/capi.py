@@ -90,6 +90,7 @@ SYMBOLS = {
     "mppi_get_outputs": (C.c_int, [_H, C.POINTER(MppiOutputs)]),
     "mppi_enable_timing": (C.c_int, [_H, C.c_int32]),
     "mppi_last_step_us": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "mppi_set_trace": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
     "mppi_test_detmath": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mppi_test_noise": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -24,10 +24,13 @@ struct MppiHandle {
     float *nominal1, *nominal2, *prev1, *prev2, *opt_v, *opt_w, *costs, *partials, *stats, *sim_traj, *sim_heading;
     float* dbg_costs;
     unsigned int* counters;
-    float* cmd_pinned;      // host pinned [2]
+    float* cmd_pinned;      // host pinned + mapped [4]: {v*, w*, sequence, 0}, written by the kernel itself
+    float* cmd_pinned_dev;  // device view of cmd_pinned
+    uint32_t host_seq;
     cudaEvent_t ev0, ev1;
     bool timing;
     bool timed_valid;
+    unsigned long long* trace;   // optional device buffer for kernel timeline stamps (mppi_set_trace)
 };
 
 static thread_local char g_cuda_err[256];
@@ -129,7 +132,8 @@ extern "C" int mppi_create(const MppiParams* params, int32_t device, int32_t max
     alloc(&h->dbg_costs, K);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->counters, R * kCounterStride * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(h->counters, 0, R * kCounterStride * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->cmd_pinned, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->cmd_pinned, 4 * sizeof(float), cudaHostAllocMapped);
+    if (e == cudaSuccess) { memset(h->cmd_pinned, 0, 4 * sizeof(float)); e = cudaHostGetDevicePointer((void**)&h->cmd_pinned_dev, h->cmd_pinned, 0); }
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e != cudaSuccess) { mppi_destroy(h); return cuda_fail(e, "mppi_create"); }
@@ -208,7 +212,7 @@ extern "C" int mppi_get_nominal(MppiHandle* h, float* u1, float* u2, int32_t n_r
 
 static int do_step(MppiHandle* h, const MppiState* state, const MppiState* states_dev, int n_rovers, int proj,
                    const float* noise, uint64_t seed, uint64_t offset, uint32_t k_begin, float* rank_partial,
-                   cudaStream_t s)
+                   cudaStream_t s, bool to_host = false)
 {
     if (!h || (proj != MPPI_PROJ_2D && proj != MPPI_PROJ_3D)) return MPPI_ERR_INVALID_ARG;
     if (!state && !states_dev) return MPPI_ERR_INVALID_ARG;
@@ -231,6 +235,8 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     a.counters = h->counters;
     a.rank_partial = rank_partial;
     a.seed = seed; a.offset = offset; a.k_begin = k_begin; a.nblocks = h->nblocks;
+    a.trace = h->trace;
+    if (to_host) { a.host_cmd = h->cmd_pinned_dev; a.host_seq = ++h->host_seq; }
     if (h->timing) CK(cudaEventRecord(h->ev0, s));
     cudaError_t e;
     if (h->pipe)
@@ -256,10 +262,22 @@ extern "C" int mppi_step_host(MppiHandle* h, const MppiState* state, int32_t pro
 {
     if (!state || !cmd_host) return MPPI_ERR_INVALID_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = do_step(h, state, nullptr, 1, proj, nullptr, seed, offset, 0u, nullptr, s);
+    int rc = do_step(h, state, nullptr, 1, proj, nullptr, seed, offset, 0u, nullptr, s, true);
     if (rc != MPPI_OK) return rc;
-    CK(cudaMemcpyAsync(h->cmd_pinned, h->stats + 6, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    // The kernel's last block stores {v*, w*, sequence} straight into mapped pinned host memory (one 16-byte
+    // store): poll the sequence word instead of paying a D2H copy plus a stream synchronisation.  The stream is
+    // queried now and then so that a faulted launch is reported instead of spinning forever.
+    volatile uint32_t* seq = reinterpret_cast<volatile uint32_t*>(h->cmd_pinned + 2);
+    const uint32_t want = h->host_seq;
+    for (unsigned spin = 1; *seq != want; ++spin) {
+        __builtin_ia32_pause();
+        if ((spin & 0x3fffu) == 0) {
+            cudaError_t q = cudaStreamQuery(s);
+            if (q == cudaSuccess) break;                       // finished: the store is visible by now
+            if (q != cudaErrorNotReady) return cuda_fail(q, "mppi_step_host");
+        }
+    }
+    if (*seq != want) CK(cudaStreamSynchronize(s));
     cmd_host[0] = h->cmd_pinned[0];
     cmd_host[1] = h->cmd_pinned[1];
     return MPPI_OK;
@@ -362,6 +380,14 @@ extern "C" int mppi_last_step_us(MppiHandle* h, float* us)
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     *us = ms * 1000.f;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_set_trace(MppiHandle* h, uint64_t* trace_dev, int32_t* nblocks_out)
+{
+    if (!h) return MPPI_ERR_INVALID_ARG;
+    h->trace = reinterpret_cast<unsigned long long*>(trace_dev);
+    if (nblocks_out) *nblocks_out = h->nblocks;
     return MPPI_OK;
 }
 

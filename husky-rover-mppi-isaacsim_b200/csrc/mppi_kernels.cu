@@ -19,6 +19,22 @@
 namespace mppi {
 namespace MPPI_NS {
 
+// ------------------------------------------------------------------ optional timeline stamps (mppi_set_trace)
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// slot: 0 entry, 1 set-up done, 2 rollout start, 3 rollout end, 4 all roles joined, 5 partial published,
+//       6 update finished (last block only), 7 SM id, 8 cost ready, 9 block min, 10 block sum + compaction,
+//       11 ticket taken, 12..15 last block: global min, ordered fold, nominal written, (v*, w*) written
+constexpr int kTraceSlots = 16;
+__device__ __forceinline__ void trace_stamp(const FusedArgs& A, int slot)
+{
+    if (A.trace != nullptr && blockIdx.y == 0) A.trace[(size_t)blockIdx.x * kTraceSlots + slot] = globaltimer_ns();
+}
+
 // ------------------------------------------------------------------ block-level helpers
 __device__ __forceinline__ void pair_min(float& c, int& k, float oc, int ok)
 {
@@ -123,51 +139,62 @@ __device__ __forceinline__ int block_compact(bool keep, int idx, float val, int 
 }
 
 // ------------------------------------------------------------------ phase 3: fold partials, finish the update
-// parts: [n][stride] softmax partials (read through L2).  Called by ONE block; smem nom1/nom2 hold the old nominal.
+// parts: [n][stride] softmax partials (read through L2).  Called by ONE block of >= 64 threads; smem nom1/nom2 hold
+// the old nominal.  `tr`: optional timeline row of this block (see trace_stamp).
 __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, const float* parts, int n,
                                      const Smem& s, float* nominal1, float* nominal2, float* prev1, float* prev2,
                                      float* opt_v, float* opt_w, float* stats, float* rank_partial,
-                                     unsigned oob_count, unsigned nan_count)
+                                     unsigned oob_count, unsigned nan_count, unsigned long long* tr,
+                                     float* host_cmd, unsigned host_seq)
 {
     const int T = p.T, tid = threadIdx.x, B = blockDim.x;
     const int stride = partial_stride(T);
 
     // 1. global min / argmin (ties -> lowest sample id)
-    float M = CUDART_INF_F;
+    float M = CUDART_INF_F, m_first = CUDART_INF_F;      // m_first: min cost of partial `tid`, reused in step 2
     int arg = 0x7fffffff;
     for (int b = tid; b < n; b += B) {
         const float mb = __ldcg(parts + (size_t)b * stride);
         const int kb = __float_as_int(__ldcg(parts + (size_t)b * stride + 2));
+        if (b == tid) m_first = mb;
         pair_min(M, arg, mb, kb);
     }
     block_min(M, arg, s);
+    if (tr != nullptr && tid == 0) tr[12] = globaltimer_ns();
 
     // 2. scale of every partial relative to M; keep the non-zero ones, in order
     int cnt = 0;
     for (int base = 0; base < n; base += B) {
         const int b = base + tid;
         float sc = 0.0f;
-        if (b < n) sc = fexp(fdiv(-(__ldcg(parts + (size_t)b * stride) - M), p.lambda));
+        if (b < n) sc = fexp(fdiv(-((base == 0 ? m_first : __ldcg(parts + (size_t)b * stride)) - M), p.lambda));
         cnt = block_compact(sc > 0.0f, b, sc, cnt, s);
     }
     __syncthreads();
 
     // 3. ordered fold; every thread recomputes S (identical on all threads), thread j < 2T owns column j
     float S = 0.0f, S2 = 0.0f;
-    for (int col0 = 0; col0 < 2 * T; col0 += B) {
-        const int col = col0 + tid;
-        float acc = 0.0f;
+    for (int col0 = 0; col0 < 2 * T; col0 += 2 * B) {        // two columns per thread and pass: loads overlap
+        const int ca = col0 + tid, cb = ca + B;
+        float acc_a = 0.0f, acc_b = 0.0f;
         S = 0.0f; S2 = 0.0f;
+#pragma unroll 2
         for (int e = 0; e < cnt; ++e) {
             const float* pb = parts + (size_t)s.list_i[e] * stride;
             const float sc = s.list_w[e];
-            S += __ldcg(pb + 1) * sc;
-            S2 += __ldcg(pb + 3) * sc * sc;
-            if (col < 2 * T) acc += __ldcg(pb + kPartialHeader + col) * sc;
+            const float ps = __ldcg(pb + 1), ps2 = __ldcg(pb + 3);
+            const float va = (ca < 2 * T) ? __ldcg(pb + kPartialHeader + ca) : 0.0f;
+            const float vb = (cb < 2 * T) ? __ldcg(pb + kPartialHeader + cb) : 0.0f;
+            S += ps * sc;
+            S2 += ps2 * sc * sc;
+            acc_a += va * sc;
+            acc_b += vb * sc;
         }
-        if (col < 2 * T) s.acc[col] = acc;
+        if (ca < 2 * T) s.acc[ca] = acc_a;
+        if (cb < 2 * T) s.acc[cb] = acc_b;
     }
     __syncthreads();
+    if (tr != nullptr && tid == 0) tr[13] = globaltimer_ns();
 
     if (rank_partial != nullptr) {           // sample-sharded mode: publish {M, S, argmin, S2, A1, A2}
         if (tid == 0) {
@@ -177,37 +204,73 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         return;
     }
 
-    // 4. updated nominal = A / S  (critics_warp.py:363-376); keep the previous one for replay
-    for (int col = tid; col < 2 * T; col += B) {
-        const float nv = fdiv(s.acc[col], S);
-        s.acc[col] = nv;
-        if (col < T) { prev1[col] = s.nom1[col]; nominal1[col] = nv; }
-        else { prev2[col - T] = s.nom2[col - T]; nominal2[col - T] = nv; }
+    // 4. updated nominal = A / S  (critics_warp.py:363-376); keep the previous one for replay.  The smem copy of
+    //    the OLD nominal is then overwritten with the filter drive u * k * (1 - a) of step 5.
+    {
+        const Recip rS = make_recip(S);
+        const float oma = 1.0f - p.opt_a;
+        for (int col = tid; col < 2 * T; col += B) {
+            const float nv = fdiv(s.acc[col], rS);
+            const float drive = nv * p.opt_k * oma;
+            if (col < T) { prev1[col] = s.nom1[col]; nominal1[col] = nv; s.nom1[col] = drive; }
+            else { prev2[col - T] = s.nom2[col - T]; nominal2[col - T] = nv; s.nom2[col - T] = drive; }
+        }
     }
     __syncthreads();
+    if (tr != nullptr && tid == 0) tr[14] = globaltimer_ns();
 
-    // 5. optimal sequence -> (v*, w*) with (opt_k, opt_a), sequential in t (MPPI_isaac.py:672-692)
-    if (tid == 0) {
-        float l = st.wheel_l, r = st.wheel_r;
-        const float oma = 1.0f - p.opt_a;
-        float v0 = 0.f, w0 = 0.f;
-        for (int t = 0; t < T; ++t) {
-            l = l * p.opt_a + s.acc[t] * p.opt_k * oma;
-            r = r * p.opt_a + s.acc[T + t] * p.opt_k * oma;
-            const float v = clampf((l + r) / 2.0f, p.v_min, p.v_max);
-            const float w = clampf(fdiv(-l + r, p.r_wheels), p.w_min, p.w_max);
-            opt_v[t] = v; opt_w[t] = w;
-            if (t == 0) { v0 = v; w0 = w; }
+    // 5. optimal sequence -> (v*, w*) with (opt_k, opt_a) (MPPI_isaac.py:672-692).  The two wheel recurrences
+    //    l <- l a + drive_l[t], r <- r a + drive_r[t] are the only sequential part: one lane of warp 0 runs the left
+    //    wheel and one lane of warp 1 the right wheel, then all threads map (l, r) -> (v, w) in parallel.  Same
+    //    operations in the same order as a one-thread loop.
+    {
+        const int right_tid = (B >= 64) ? 32 : 0;        // a second warp when there is one
+        for (int side = 0; side < 2; ++side) {
+            if (tid != (side == 0 ? 0 : right_tid)) continue;
+            float* d = (side == 0) ? s.nom1 : s.nom2;
+            float x = (side == 0) ? st.wheel_l : st.wheel_r;
+            constexpr int N = 8;                         // steps per register batch; the next batch is loaded
+            float cur[N], nxt[N];                        // BEFORE the current one is stored (in place)
+#pragma unroll
+            for (int i = 0; i < N; ++i) cur[i] = (i < T) ? d[i] : 0.0f;
+            for (int t0 = 0; t0 < T; t0 += N) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) nxt[i] = (t0 + N + i < T) ? d[t0 + N + i] : 0.0f;
+#pragma unroll
+                for (int i = 0; i < N; ++i) { x = x * p.opt_a + cur[i]; cur[i] = x; }
+#pragma unroll
+                for (int i = 0; i < N; ++i) if (t0 + i < T) d[t0 + i] = cur[i];
+#pragma unroll
+                for (int i = 0; i < N; ++i) cur[i] = nxt[i];
+            }
         }
+    }
+    __syncthreads();
+    {
+        const Recip rw = make_recip(p.r_wheels);
+        for (int t = tid; t < T; t += B) {
+            const float l = s.nom1[t], r = s.nom2[t];
+            const float v = clampf((l + r) / 2.0f, p.v_min, p.v_max);
+            const float w = clampf(fdiv(-l + r, rw), p.w_min, p.w_max);
+            opt_v[t] = v; opt_w[t] = w;
+            if (t == 0) {
+                stats[6] = v; stats[7] = w;                 // the command, contiguous for one 8-byte D2H
+                // zero-copy result for mppi_step_host: ONE 16-byte store {v*, w*, sequence number, 0} into mapped
+                // pinned host memory; the host polls the sequence word
+                if (host_cmd != nullptr)
+                    *reinterpret_cast<float4*>(host_cmd) = make_float4(v, w, __uint_as_float(host_seq), 0.0f);
+            }
+        }
+    }
+    if (tid == 0) {
         stats[0] = M;
         stats[1] = __int_as_float(arg);
         stats[2] = S;
         stats[3] = __uint_as_float(oob_count);
         stats[4] = __uint_as_float(nan_count);
         stats[5] = fdiv(S * S, S2);           // effective sample size
-        stats[6] = v0;                         // the command, contiguous for one 8-byte D2H
-        stats[7] = w0;
     }
+    if (tr != nullptr && tid == 0) tr[15] = globaltimer_ns();
 }
 
 // ------------------------------------------------------------------ phases 2 + 3, shared by both fused kernels
@@ -227,19 +290,41 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
     // ---------------- phase 2: block softmax partial
     float m_b = cost;
     int arg_b = valid ? (int)kg : 0x7fffffff;
-    block_min(m_b, arg_b, s);
-    float w = 0.0f;
-    if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));   // critics_warp.py:346-347
-    float s_b = w, s2_b = w * w;
-    block_sum2(s_b, s2_b, s);
-    const int n_e = block_compact(w > 0.0f, k_in_block, w, 0, s);
-    __syncthreads();
+    float w = 0.0f, s_b, s2_b;
+    int n_e;
+    if (tid == 0) trace_stamp(A, 8);
+    if (spb == 32) {
+        // all samples of the block live in warp 0: warp-level reductions, one barrier to publish the list
+        if (tid < 32) {
+            warp_min(m_b, arg_b);
+            if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));   // critics_warp.py:346-347
+            s_b = warp_sum(w);
+            s2_b = warp_sum(w * w);
+            const unsigned mask = __ballot_sync(0xffffffffu, w > 0.0f);
+            if (w > 0.0f) {
+                const int pos = __popc(mask & ((1u << tid) - 1u));
+                s.list_i[pos] = k_in_block;
+                s.list_w[pos] = w;
+            }
+            if (tid == 0) { s.red_i[62] = __popc(mask); s.red_f[0] = m_b; s.red_f[1] = s_b; s.red_f[2] = s2_b; s.red_i[0] = arg_b; }
+        }
+        __syncthreads();
+        n_e = s.red_i[62]; m_b = s.red_f[0]; s_b = s.red_f[1]; s2_b = s.red_f[2]; arg_b = s.red_i[0];
+    } else {
+        block_min(m_b, arg_b, s);
+        if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));       // critics_warp.py:346-347
+        s_b = w; s2_b = w * w;
+        block_sum2(s_b, s2_b, s);
+        n_e = block_compact(w > 0.0f, k_in_block, w, 0, s);
+        __syncthreads();
+    }
+    if (tid == 0) trace_stamp(A, 10);
 
     const int stride = partial_stride(T);
     float* part = A.partials + ((size_t)rover * A.nblocks + blockIdx.x) * stride;
     {
         const int P = (T + 1) >> 1;                       // step pairs
-        const int G = (B >= 2 * P) ? B / P : 1;           // entry groups working in parallel
+        const int G = (B >= 2 * P && n_e > 1) ? B / P : 1;   // entry groups working in parallel
         const int g = tid / P, pr0 = tid - g * P;
         for (int pbase = 0; pbase < P; pbase += B) {      // one pass unless P > B
             const int pr = (G > 1) ? pr0 : pbase + tid;
@@ -294,18 +379,21 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
             if (G > 1) break;
         }
     }
-    if (tid == 0) { part[0] = m_b; part[1] = s_b; part[2] = __int_as_float(arg_b); part[3] = s2_b; }
+    if (tid == 0) { part[0] = m_b; part[1] = s_b; part[2] = __int_as_float(arg_b); part[3] = s2_b; trace_stamp(A, 5); }
 
     // ---------------- phase 3: last block folds everything
-    __threadfence();
+    // publish: the barrier orders every thread's partial stores before thread 0's gpu-scope release
     __syncthreads();
     if (tid == 0) {
-        const unsigned ticket = atomicAdd(&A.counters[rover * kCounterStride + 0], 1u);
+        unsigned ticket;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;"
+                     : "=r"(ticket) : "l"(&A.counters[rover * kCounterStride + 0]) : "memory");
         s.red_i[63] = (ticket == (unsigned)(A.nblocks - 1));
+        trace_stamp(A, 11);
     }
     __syncthreads();
     if (!s.red_i[63]) return;
-    __threadfence();
+    // every partial was published before its block's fence + ticket; the reads below go to L2 (__ldcg)
 
     const unsigned oob_count = __ldcg(&A.counters[rover * kCounterStride + 1]);
     const unsigned nan_count = __ldcg(&A.counters[rover * kCounterStride + 2]);
@@ -313,8 +401,11 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
                          nominal1, nominal2, A.prev1 + (size_t)rover * T, A.prev2 + (size_t)rover * T,
                          A.opt_v + (size_t)rover * T, A.opt_w + (size_t)rover * T,
                          A.stats + (size_t)rover * kStatsStride,
-                         A.rank_partial ? A.rank_partial + (size_t)rover * stride : nullptr, oob_count, nan_count);
+                         A.rank_partial ? A.rank_partial + (size_t)rover * stride : nullptr, oob_count, nan_count,
+                         (A.trace != nullptr && rover == 0) ? A.trace + (size_t)blockIdx.x * kTraceSlots : nullptr,
+                         (rover == 0) ? A.host_cmd : nullptr, A.host_seq);
     if (tid == 0) {                                       // re-arm for the next launch
+        trace_stamp(A, 6);
         A.counters[rover * kCounterStride + 0] = 0u;
         A.counters[rover * kCounterStride + 1] = 0u;
         A.counters[rover * kCounterStride + 2] = 0u;
@@ -331,6 +422,14 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
     const int T = p.T, K = p.K, B = blockDim.x, tid = threadIdx.x;
     const int rover = blockIdx.y;
     const Smem s = carve(smem_raw, T, B, A.nblocks);
+    if (tid == 0) {
+        trace_stamp(A, 0);
+        if (A.trace != nullptr && rover == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            A.trace[(size_t)blockIdx.x * kTraceSlots + 7] = smid;
+        }
+    }
 
     const MppiState st = (A.states != nullptr) ? A.states[rover] : A.state;
     const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
@@ -352,6 +451,7 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
     // ---------------- phase 1: rollout + critics
     float cost = CUDART_INF_F;
     unsigned my_oob = 0, my_nan = 0;
+    if (tid == 0) { trace_stamp(A, 1); trace_stamp(A, 2); }
     if (valid) {
         SampleAcc a;
         sample_init<PROJ>(st, ter, a);
@@ -378,9 +478,10 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
         }
         cost = sample_cost(p, sc, a, nullptr);
         A.costs[(size_t)rover * K + k_local] = cost;
-        my_oob = (unsigned)a.oob;
+        my_oob = (unsigned)(a.oob + unit_violation(a.dev));
         if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }   // a NaN rollout gets zero weight
     }
+    if (tid == 0) { trace_stamp(A, 3); trace_stamp(A, 4); }
     block_update<INJECT>(A, st, nk, s, rover, B, valid, tid, cost, my_oob, my_nan, nominal1, nominal2);
 }
 
@@ -454,6 +555,14 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     const int rover = blockIdx.y;
     const Smem s = carve(smem_raw, T, kPipeThreads, A.nblocks);
     PipeSmem& ps = *reinterpret_cast<PipeSmem*>(smem_raw + pipe_smem_offset_floats(T, A.nblocks));
+    if (tid == 0) {
+        trace_stamp(A, 0);
+        if (A.trace != nullptr && rover == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            A.trace[(size_t)blockIdx.x * kTraceSlots + 7] = smid;
+        }
+    }
 
     const MppiState st = (A.states != nullptr) ? A.states[rover] : A.state;
     const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
@@ -472,6 +581,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         }
     }
     __syncthreads();
+    if (tid == 0) trace_stamp(A, 1);
 
     const int k_local = blockIdx.x * 32 + lane;
     const bool valid = k_local < K;
@@ -534,11 +644,13 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         // ---- chain: the recurrence
         float x = st.x, y = st.y;
         float3 prev = make_float3(st.hx, st.hy, st.hz), n;
+        float dev = 0.0f;
         if (PROJ == MPPI_PROJ_3D) {
             int i0, j0;
             const Quad q = corners(ter, x, y, i0, j0, oob);
             prev = tangent(normal_on_grid(q, ter.res), prev);
         }
+        if (lane == 0) trace_stamp(A, 2);
         for (int c = 0; c < nchunks; ++c) {
             const int sg = c % kPipeStages;
             const unsigned ph = (c / kPipeStages) & 1;
@@ -550,7 +662,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                 if (t < T) {
                     const float v = ps.ring_a[sg][i][0][lane];
                     const float sn = ps.ring_a[sg][i][1][lane], cs = ps.ring_a[sg][i][2][lane];
-                    role_chain<PROJ>(p, ter, x, y, prev, v, sn, cs, n, oob);
+                    role_chain<PROJ>(p, ter, x, y, prev, v, sn, cs, n, oob, dev);
                     float* o = &ps.ring_b[sg][i][0][lane];
                     o[0] = x; o[32] = y;
                     if ((i & 1) == 0) {                  // only even steps feed the wheel / slope role
@@ -562,6 +674,8 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             mbar_arrive(&ps.empty_a[sg]);
             mbar_arrive(&ps.full_b[sg]);
         }
+        oob += unit_violation(dev);
+        if (lane == 0) trace_stamp(A, 3);
     } else if (role == ROLE_WHEELS) {
         // ---- wheels + slope critic
         float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e;
@@ -601,6 +715,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     }
     ps.oob[role][lane] = oob;
     __syncthreads();
+    if (tid == 0) trace_stamp(A, 4);
 
     // ---- cost (critics_warp.py:325-329), owned by warp 0
     float cost = CUDART_INF_F;
@@ -627,7 +742,7 @@ __global__ void __launch_bounds__(kMaxBlock) mppi_combine_kernel(const __grid_co
     for (int t = threadIdx.x; t < T; t += B) { s.nom1[t] = A.nominal1[t]; s.nom2[t] = A.nominal2[t]; }
     __syncthreads();
     combine_and_finalize(A.p, A.state, A.parts, A.n_parts, s, A.nominal1, A.nominal2, A.prev1, A.prev2,
-                         A.opt_v, A.opt_w, A.stats, nullptr, 0u, 0u);
+                         A.opt_v, A.opt_w, A.stats, nullptr, 0u, 0u, nullptr, nullptr, 0u);
 }
 
 // ------------------------------------------------------------------ validation / visualiser dump (unfused view)
@@ -696,17 +811,18 @@ __global__ void mppi_sim_kernel(const __grid_constant__ SimArgs A)
     const MppiParams& p = A.p;
     const Terr ter = make_terr(A.terrain);
     int oob = 0, i, j;
+    float dev = 0.0f;
     float x = A.state.x, y = A.state.y;
     Quad q = corners(ter, x, y, i, j, oob);
     float3 n = normal_on_grid(q, ter.res);
     float3 prev = tangent(n, make_float3(A.state.hx, A.state.hy, A.state.hz));
     for (int t = 0; t < p.T; ++t) {
-        update_position(x, y, prev, A.opt_v[t], p.dt, oob);
+        update_position(x, y, prev, A.opt_v[t], p.dt, dev);
         q = corners(ter, x, y, i, j, oob);
         const float h = bilinear(x, y, q, ter.rres);
         n = normal_on_grid(q, ter.res);
         prev = tangent(n, prev);
-        const float3 cur = update_orientation(prev, A.opt_w[t], n, p.dt, oob);
+        const float3 cur = update_orientation(prev, A.opt_w[t], n, p.dt, dev);
         A.sim_traj[3 * t] = x; A.sim_traj[3 * t + 1] = y; A.sim_traj[3 * t + 2] = h;
         A.sim_heading[3 * t] = cur.x; A.sim_heading[3 * t + 1] = cur.y; A.sim_heading[3 * t + 2] = cur.z;
         prev = cur;

@@ -38,6 +38,9 @@ struct FusedArgs {
     uint64_t seed, offset;
     uint32_t k_begin;                 // first global sample id of this rank
     int32_t nblocks;                  // grid.x
+    unsigned long long* trace;        // optional device [nblocks][16] %globaltimer stamps (profiling aid), or nullptr
+    float* host_cmd;                  // optional mapped pinned host memory [4]: {v*, w*, sequence, 0} (mppi_step_host)
+    uint32_t host_seq;                // sequence number stored with the command
 };
 
 struct CombineArgs {

@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Turns an `ncu --set full --import-source on` report into the markdown summary committed under profiles/.
+
+  python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_<what>.md
+
+Runs here (no GPU needed: `ncu -i` only reads the report).
+"""
+from __future__ import annotations
+
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+RAW_KEYS = [
+    "gpu__time_duration.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
+    "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "launch__occupancy_limit_warps", "launch__waves_per_multiprocessor",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed.sum.per_cycle_elapsed", "sm__inst_executed.sum.per_cycle_active", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "l1tex__t_bytes.sum.per_second", "lts__t_bytes.sum.per_second", "lts__t_bytes.sum",
+    "lts__t_sectors_op_read.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__average_warp_latency_per_inst_issued.ratio",
+]
+
+
+def ncu_csv(rep, page):
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
+def main():
+    rep = sys.argv[1]
+    raw = ncu_csv(rep, "raw")
+    hdr, units = raw[0], raw[1]
+    print(f"# ncu summary of `{rep.split('/')[-1]}`\n")
+    print("`ncu --set full --clock-control none --import-source on` (one replayed launch per row; times under the "
+          "profiler are cold-cache and serialised and are NOT bench numbers).\n")
+    for r in raw[2:]:
+        d = dict(zip(hdr, r))
+        print(f"## launch {d.get('ID')}: `{d.get('Kernel Name')}` grid {d.get('Grid Size')} block {d.get('Block Size')}\n")
+        print("| metric | value | unit |\n|---|---|---|")
+        u = dict(zip(hdr, units))
+        for k in RAW_KEYS:
+            if k in d and d[k] != "":
+                print(f"| {k} | {d[k]} | {u[k]} |")
+        st = [(h, float(d[h])) for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and d[h]]
+        st.sort(key=lambda x: -x[1])
+        print("\nWarp states per issue slot (warps per issue-active cycle; `selected` = issuing):\n")
+        print("| state | warps |\n|---|---|")
+        for h, v in st[:9]:
+            print(f"| {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} | {v:.3f} |")
+        print()
+    src = ncu_csv(rep, "source")
+    starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"]
+    if not starts:
+        return
+    s0 = starts[0]
+    end = starts[1] if len(starts) > 1 else len(src)
+    h = src[s0 + 1]
+    ix = {n: i for i, n in enumerate(h)}
+    data = src[s0 + 2:end]
+    reasons = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
+    tot = sum(int(r[ix["# Samples"]]) for r in data)
+    agg = collections.Counter()
+    ops = collections.Counter()
+    for r in data:
+        for n in reasons:
+            agg[n] += int(r[ix[n]] or 0)
+        toks = r[ix["Source"]].split()
+        if toks:
+            op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
+            ops[op.split(".")[0]] += int(r[ix["Instructions Executed"]] or 0)
+    print(f"## SASS-level sampling of the first launch ({len(data)} instructions, {tot} samples)\n")
+    print("| stall reason | samples | share |\n|---|---|---|")
+    for n, v in agg.most_common(10):
+        print(f"| {n} | {v} | {100.0 * v / max(1, sum(agg.values())):.1f} % |")
+    nexec = sum(ops.values())
+    print(f"\nExecuted warp-instructions by opcode ({nexec} total):\n")
+    print("| opcode | warp-instructions | share |\n|---|---|---|")
+    for op, v in ops.most_common(18):
+        print(f"| {op} | {v} | {100.0 * v / max(1, nexec):.1f} % |")
+    print("\nTop 25 instructions by samples:\n")
+    print("| # | SASS | samples | executed | dominant stalls |\n|---|---|---|---|---|")
+    top = sorted(range(len(data)), key=lambda i: -int(data[i][ix["# Samples"]]))[:25]
+    for i in sorted(top):
+        r = data[i]
+        rs = sorted(((n, int(r[ix[n]] or 0)) for n in reasons), key=lambda x: -x[1])[:2]
+        rs = ", ".join(f"{n.replace('stall_', '')} {v}" for n, v in rs if v)
+        print(f"| {i} | `{r[ix['Source']].strip()[:64]}` | {r[ix['# Samples']]} | {r[ix['Instructions Executed']]} | {rs} |")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Timeline of one fused MPPI launch from the kernel's own %globaltimer stamps (mppi_set_trace).
+
+  python tools/timeline.py [--workload C2] [--math strict] [--variant auto] [--K 0] [--T 0] [--reps 20]
+
+Prints, per phase, the min / median / max over blocks (microseconds relative to the first block's entry) and the
+CUDA-event duration of the same launches, as one JSON object.  Diagnostic only (GPU needed).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import dataclasses
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+PHASES = ["entry", "setup_done", "rollout_start", "rollout_end", "roles_joined", "partial_published", "update_done", "smid",
+          "cost_ready", "block_min", "block_sum_compact", "ticket", "g_min", "g_fold", "g_nominal", "g_cmd"]
+NS = 16
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--math", default="strict")
+    ap.add_argument("--variant", default="auto")
+    ap.add_argument("--K", type=int, default=0)
+    ap.add_argument("--T", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between launches")
+    ap.add_argument("--dump", default="", help="save the per-block stamps of every repetition as .npy [reps, nblocks, 8]")
+    a = ap.parse_args()
+
+    import torch
+    from mppi_b200 import capi, synthetic as syn
+    from mppi_b200.core import Core, make_state
+
+    w = syn.WORKLOADS[a.workload]
+    if a.K or a.T:
+        w = dataclasses.replace(w, K=a.K or w.K, T=a.T or w.T)
+    dev = torch.device("cuda", 0)
+    dem = syn.crater_dem(w.grid_size, w.half_width).to(dev)
+    cm = torch.from_numpy(syn.rock_costmap(w.costmap_size, w.half_width)).to(dev)
+    start, goal = syn.workload_start_goal(w)
+    core = Core(w.K, w.T, math=a.math,
+                variant={"auto": capi.VARIANT_AUTO, "mono": capi.VARIANT_MONO, "pipe": capi.VARIANT_PIPE}[a.variant])
+    core.set_terrain(dem, w.half_width, cm)
+    st = make_state(start[0], start[1], goal_x=goal[0], goal_y=goal[1])
+    nb = C.c_int32()
+    capi.check(core.L.mppi_set_trace(core.h, None, C.byref(nb)), "mppi_set_trace")
+    trace = torch.zeros((nb.value, NS), dtype=torch.int64, device=dev)
+    capi.check(core.L.mppi_set_trace(core.h, trace.data_ptr(), None), "mppi_set_trace")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for i in range(5):
+        core.step(st, capi.PROJ_3D, None, 42, i)
+    torch.cuda.synchronize()
+    rows, evt, raw_rows = [], [], []
+    for i in range(a.reps):
+        if not a.no_flush:
+            flush.fill_(i & 255)
+        trace.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        core.step(st, capi.PROJ_3D, None, 42, 100 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        evt.append(e0.elapsed_time(e1) * 1e3)
+        t = trace.cpu().numpy().astype(np.float64)
+        t0 = t[:, 0].min()
+        rel = (t - t0) / 1e3
+        rel[t == 0] = np.nan
+        rel[:, 7] = t[:, 7]
+        rows.append(rel)
+        raw_rows.append(rel)
+    if a.dump:
+        np.save(a.dump, np.stack(raw_rows))
+    rel = np.stack(rows)                                  # [reps, nblocks, 7]
+    out = {"workload": w.name, "K": w.K, "T": w.T, "math": a.math, "variant": a.variant, "nblocks": int(nb.value),
+           "event_us": {"median": float(np.median(evt)), "min": float(np.min(evt))},
+           "sms_used": int(len(np.unique(trace[:, 7].cpu().numpy()))), "phases_us": {}}
+    import warnings
+    warnings.simplefilter("ignore")
+    for j, name in enumerate(PHASES):
+        if name == "smid":
+            continue
+        x = rel[:, :, j]
+        out["phases_us"][name] = {"first": float(np.nanmedian(np.nanmin(x, axis=1))),
+                                  "median": float(np.nanmedian(x)),
+                                  "last": float(np.nanmedian(np.nanmax(x, axis=1)))}
+    dur = rel[:, :, 3] - rel[:, :, 2]
+    out["rollout_us_per_block"] = {"min": float(np.nanmin(dur)), "median": float(np.nanmedian(dur)),
+                                   "max": float(np.nanmax(dur)), "per_step_ns_median": float(np.nanmedian(dur) * 1e3 / w.T)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -7,8 +7,11 @@
  *
  * Not the product: only tests/, smoke() and bench.py's CPU-baseline legs load this.
  *
- * Parity status: UNPINNED by the reference's own tests (it has none for this path); see
- * oracle/README.md for what this file is pinned against instead.
+ * Parity status: the reference has no tests for this path; this file is pinned against outputs of the
+ * reference's own controller + kernel sources executed in the build container under oracle/warp_shim.py
+ * (tests/golden/reference_mppi_steps.npz, tests/test_reference_kernels_golden.py) -- u, v, omega bit-identical,
+ * everything else to ~1e-7.  warp-lang's own arithmetic (wp.randn, libdevice bit patterns) stays unpinned; see
+ * oracle/README.md.
  *
  * Indexing note: the reference computes per-sample offsets in float32 (critics_warp.py:325-329,
  * `wp.float(tid)*iterations`), exact only while K*T < 2^24.  This restatement uses integers,

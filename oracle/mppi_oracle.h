@@ -4,10 +4,11 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product path (husky-rover-mppi-isaacsim_b200/) never does.
  *
- * Parity status: the reference holds NO golden vectors for this path:
- * "parity unpinned" by the reference's own tests.  The pins used instead are listed in
- * oracle/README.md (function-level goldens generated from the reference's CPU script,
- * trajectory_2D.csv, Random123 Philox KATs, and a second independent NumPy restatement).
+ * Parity status: the reference holds no golden vectors for this path.  The oracle
+ * is pinned against outputs of the reference's own controller + kernel sources run in the build container under
+ * oracle/warp_shim.py (tests/golden/reference_mppi_steps.npz) plus the pins listed in oracle/README.md
+ * (function-level goldens from the reference's CPU script, trajectory_2D.csv, Random123 Philox KATs, a second
+ * independent NumPy restatement).  warp-lang's own arithmetic (wp.randn, libdevice) stays unpinned.
  */
 #ifndef MPPI_ORACLE_H
 #define MPPI_ORACLE_H

@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--math", default="strict", choices=["strict", "fast"])
     ap.add_argument("--variant", default="auto", choices=["auto", "mono", "pipe"], help="fused-kernel variant")
+    ap.add_argument("--exchange", default=os.environ.get("MPPI_SHARD_EXCHANGE", "p2p"), choices=["p2p", "nccl"],
+                    help="multi-GPU exchange of the softmax partials: fused peer-memory stores or NCCL all-gather")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -227,7 +229,7 @@ def main():
     cm = torch.from_numpy(cm_np).to(dev)
     core.set_terrain(dem, w.half_width, cm)
     state = make_state(start[0], start[1], (1.0, 0.0, 0.0), goal_x=goal[0], goal_y=goal[1])
-    stepper = SampleShardedStepper(core, K_total) if n_gpus > 1 else None
+    stepper = SampleShardedStepper(core, K_total, transport=args.exchange) if n_gpus > 1 else None
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     do_flush = not args.no_flush
     seed = 42
@@ -302,8 +304,7 @@ def main():
                 flush_buf.fill_(i & 0xff)
             barrier()
             t0 = time.perf_counter()
-            one_step(20000 + i)
-            _ = core.stats[0, 6:8].cpu()
+            stepper.step_host(state, capi.PROJ_3D, seed, 20000 + i)
             e2e_t.append(time.perf_counter() - t0)
         t = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -350,13 +351,15 @@ def main():
                        "math": args.math, "variant": args.variant, "noise": "in-kernel Philox4x32-10 + Box-Muller", "proj": "3d",
                        "l2": "flushed between timed iterations (256 MiB fill)" if do_flush else "warm",
                        "parallelism": "single GPU" if n_gpus == 1 else
-                       f"sample-sharded x{n_gpus}, all-gather of {core.partial_floats() * 4} B softmax partial"},
+                       (f"sample-sharded x{n_gpus}, {core.partial_floats() * 4} B softmax partial per rank exchanged "
+                        + ("inside the fused launch over NVLink peer memory (CUDA IPC), no collective call"
+                           if args.exchange == "p2p" else "with one NCCL all-gather + combine kernel"))},
             "latency_us": {"p50": float(np.median(per_step_ms) * 1e3), "p99": float(np.percentile(per_step_ms, 99) * 1e3),
                            "mean": float(per_step_ms.mean() * 1e3)},
             "warm_l2": {"ms_per_step": float(warm_ms.mean()), "p50_us": float(np.median(warm_ms) * 1e3),
                         "value": K_total * T / float(warm_ms.mean() * 1e-3)},
             "e2e": e2e,
-            "gpu_launches": args.steps * (1 if n_gpus == 1 else 2),
+            "gpu_launches": args.steps * (1 if (n_gpus == 1 or args.exchange == "p2p") else 2),
             "roofline": roofline,
             "clocks": clocks,
             "wall_s": wall_s,

@@ -84,6 +84,12 @@ SYMBOLS = {
                                     C.c_uint32, C.c_void_p, C.c_void_p]),
     "mppi_combine_partials": (C.c_int, [_H, C.POINTER(MppiState), C.c_void_p, C.c_int32, C.c_void_p]),
     "mppi_partial_floats": (C.c_int, [C.c_int32]),
+    "mppi_comm_export": (C.c_int, [_H, C.c_int32, C.c_void_p]),
+    "mppi_comm_connect": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
+    "mppi_step_sharded_host": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32,
+                                         C.c_void_p, C.c_void_p]),
+    "mppi_step_sharded": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64,
+                                    C.c_uint32, C.c_void_p]),
     "mppi_sim_rollout": (C.c_int, [_H, C.POINTER(MppiState), C.c_void_p]),
     "mppi_debug_dump": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32,
                                   C.POINTER(MppiDebugDump), C.c_void_p]),

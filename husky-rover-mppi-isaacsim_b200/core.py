@@ -116,6 +116,29 @@ class Core:
         capi.check(self.L.mppi_combine_partials(self.h, C.byref(state), parts.data_ptr(), n_parts,
                                                 self._stream(stream)), "mppi_combine_partials")
 
+    # ---- sample-sharded step with the exchange fused into the launch (NVLink peer memory, CUDA IPC)
+    def comm_export(self, world: int) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        capi.check(self.L.mppi_comm_export(self.h, world, buf), "mppi_comm_export")
+        return bytes(buf)
+
+    def comm_connect(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == 64 * world
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        capi.check(self.L.mppi_comm_connect(self.h, rank, world, buf), "mppi_comm_connect")
+
+    def step_sharded(self, state, k_begin: int, proj: int = capi.PROJ_3D, noise: Optional[torch.Tensor] = None,
+                     seed: int = 0, offset: int = 0, stream=None):
+        capi.check(self.L.mppi_step_sharded(self.h, C.byref(state), proj,
+                                            noise.data_ptr() if noise is not None else None, seed, offset, k_begin,
+                                            self._stream(stream)), "mppi_step_sharded")
+
+    def step_sharded_host(self, state, k_begin: int, proj: int = capi.PROJ_3D, seed: int = 0, offset: int = 0,
+                          stream=None):
+        capi.check(self.L.mppi_step_sharded_host(self.h, C.byref(state), proj, seed, offset, k_begin, self._cmd,
+                                                 self._stream(stream)), "mppi_step_sharded_host")
+        return self._cmd[0], self._cmd[1]
+
     def sim_rollout(self, state, stream=None):
         capi.check(self.L.mppi_sim_rollout(self.h, C.byref(state), self._stream(stream)), "mppi_sim_rollout")
 

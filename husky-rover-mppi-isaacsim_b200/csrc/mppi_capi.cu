@@ -31,6 +31,10 @@ struct MppiHandle {
     bool timing;
     bool timed_valid;
     unsigned long long* trace;   // optional device buffer for kernel timeline stamps (mppi_set_trace)
+    // sample-sharded multi-GPU exchange over peer memory (mppi_comm_*)
+    void* comm_local;            // this rank's exchange allocation: [2][world][stride] floats + [2][world] flags
+    void* comm_peer[kMaxRanks];  // peers' allocations opened with CUDA IPC (nullptr for this rank)
+    PeerComm peers;
 };
 
 static thread_local char g_cuda_err[256];
@@ -148,6 +152,8 @@ extern "C" int mppi_destroy(MppiHandle* h)
     float* bufs[] = { h->nominal1, h->nominal2, h->prev1, h->prev2, h->opt_v, h->opt_w, h->costs, h->partials,
                       h->stats, h->sim_traj, h->sim_heading, h->dbg_costs };
     for (float* b : bufs) if (b) cudaFree(b);
+    for (int r = 0; r < kMaxRanks; ++r) if (h->comm_peer[r]) cudaIpcCloseMemHandle(h->comm_peer[r]);
+    if (h->comm_local) cudaFree(h->comm_local);
     if (h->counters) cudaFree(h->counters);
     if (h->cmd_pinned) cudaFreeHost(h->cmd_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -212,7 +218,7 @@ extern "C" int mppi_get_nominal(MppiHandle* h, float* u1, float* u2, int32_t n_r
 
 static int do_step(MppiHandle* h, const MppiState* state, const MppiState* states_dev, int n_rovers, int proj,
                    const float* noise, uint64_t seed, uint64_t offset, uint32_t k_begin, float* rank_partial,
-                   cudaStream_t s, bool to_host = false)
+                   cudaStream_t s, bool to_host = false, bool sharded = false)
 {
     if (!h || (proj != MPPI_PROJ_2D && proj != MPPI_PROJ_3D)) return MPPI_ERR_INVALID_ARG;
     if (!state && !states_dev) return MPPI_ERR_INVALID_ARG;
@@ -237,6 +243,7 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     a.seed = seed; a.offset = offset; a.k_begin = k_begin; a.nblocks = h->nblocks;
     a.trace = h->trace;
     if (to_host) { a.host_cmd = h->cmd_pinned_dev; a.host_seq = ++h->host_seq; }
+    if (sharded) { a.peers = h->peers; a.peers.seq = ++h->peers.seq; }
     if (h->timing) CK(cudaEventRecord(h->ev0, s));
     cudaError_t e;
     if (h->pipe)
@@ -257,16 +264,11 @@ extern "C" int mppi_step(MppiHandle* h, const MppiState* state, int32_t proj, co
     return do_step(h, state, nullptr, 1, proj, noise_dev, seed, offset, 0u, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int mppi_step_host(MppiHandle* h, const MppiState* state, int32_t proj, uint64_t seed, uint64_t offset,
-                              float* cmd_host, void* stream)
+// The kernel's last block stores {v*, w*, sequence} straight into mapped pinned host memory (one 16-byte store):
+// poll the sequence word instead of paying a D2H copy plus a stream synchronisation.  The stream is queried now
+// and then so that a faulted launch is reported instead of spinning forever.
+static int wait_host_command(MppiHandle* h, float* cmd_host, cudaStream_t s)
 {
-    if (!state || !cmd_host) return MPPI_ERR_INVALID_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = do_step(h, state, nullptr, 1, proj, nullptr, seed, offset, 0u, nullptr, s, true);
-    if (rc != MPPI_OK) return rc;
-    // The kernel's last block stores {v*, w*, sequence} straight into mapped pinned host memory (one 16-byte
-    // store): poll the sequence word instead of paying a D2H copy plus a stream synchronisation.  The stream is
-    // queried now and then so that a faulted launch is reported instead of spinning forever.
     volatile uint32_t* seq = reinterpret_cast<volatile uint32_t*>(h->cmd_pinned + 2);
     const uint32_t want = h->host_seq;
     for (unsigned spin = 1; *seq != want; ++spin) {
@@ -281,6 +283,16 @@ extern "C" int mppi_step_host(MppiHandle* h, const MppiState* state, int32_t pro
     cmd_host[0] = h->cmd_pinned[0];
     cmd_host[1] = h->cmd_pinned[1];
     return MPPI_OK;
+}
+
+extern "C" int mppi_step_host(MppiHandle* h, const MppiState* state, int32_t proj, uint64_t seed, uint64_t offset,
+                              float* cmd_host, void* stream)
+{
+    if (!state || !cmd_host) return MPPI_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = do_step(h, state, nullptr, 1, proj, nullptr, seed, offset, 0u, nullptr, s, true);
+    if (rc != MPPI_OK) return rc;
+    return wait_host_command(h, cmd_host, s);
 }
 
 extern "C" int mppi_step_batched(MppiHandle* h, const MppiState* states_dev, int32_t n_rovers, int32_t proj,
@@ -313,6 +325,68 @@ extern "C" int mppi_combine_partials(MppiHandle* h, const MppiState* state, cons
                                                   : strict::launch_combine(a, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch_combine");
     return MPPI_OK;
+}
+
+// ---------------------------------------------------------------- sample-sharded step over peer memory
+static size_t comm_floats(int world, int T) { return (size_t)2 * world * partial_stride(T); }
+
+extern "C" int mppi_comm_export(MppiHandle* h, int32_t world, unsigned char* ipc_handle_out)
+{
+    if (!h || world < 1 || world > kMaxRanks || !ipc_handle_out) return MPPI_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->comm_local) return MPPI_ERR_INVALID_ARG;             // already exported
+    const size_t bytes = comm_floats(world, h->T_cap) * sizeof(float) + (size_t)2 * world * sizeof(unsigned);
+    CK(cudaMalloc(&h->comm_local, bytes));
+    CK(cudaMemset(h->comm_local, 0, bytes));
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->comm_local));
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &mh, sizeof(mh));
+    return MPPI_OK;
+}
+
+extern "C" int mppi_comm_connect(MppiHandle* h, int32_t rank, int32_t world, const unsigned char* ipc_handles)
+{
+    if (!h || !h->comm_local || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !ipc_handles)
+        return MPPI_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    memset(&h->peers, 0, sizeof(h->peers));
+    for (int r = 0; r < world; ++r) {
+        void* base = h->comm_local;
+        if (r != rank) {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, ipc_handles + (size_t)r * sizeof(mh), sizeof(mh));
+            CK(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+            h->comm_peer[r] = base;
+        }
+        h->peers.x[r] = static_cast<float*>(base);
+        h->peers.f[r] = reinterpret_cast<unsigned*>(static_cast<float*>(base) + comm_floats(world, h->T_cap));
+    }
+    h->peers.rank = rank;
+    h->peers.world = world;
+    h->peers.seq = 0;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_step_sharded(MppiHandle* h, const MppiState* state, int32_t proj, const float* noise_dev,
+                                 uint64_t seed, uint64_t offset, uint32_t k_begin, void* stream)
+{
+    if (!h || !state || h->peers.world < 1) return MPPI_ERR_INVALID_ARG;
+    if (h->p.T != h->T_cap) return MPPI_ERR_UNSUPPORTED;        // the exchange slots are laid out for T_cap
+    return do_step(h, state, nullptr, 1, proj, noise_dev, seed, offset, k_begin, nullptr, (cudaStream_t)stream,
+                   false, true);
+}
+
+extern "C" int mppi_step_sharded_host(MppiHandle* h, const MppiState* state, int32_t proj, uint64_t seed,
+                                      uint64_t offset, uint32_t k_begin, float* cmd_host, void* stream)
+{
+    if (!h || !state || !cmd_host || h->peers.world < 1) return MPPI_ERR_INVALID_ARG;
+    if (h->p.T != h->T_cap) return MPPI_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = do_step(h, state, nullptr, 1, proj, nullptr, seed, offset, k_begin, nullptr, s, true, true);
+    if (rc != MPPI_OK) return rc;
+    return wait_host_command(h, cmd_host, s);
 }
 
 extern "C" int mppi_sim_rollout(MppiHandle* h, const MppiState* state, void* stream)

@@ -145,7 +145,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
                                      const Smem& s, float* nominal1, float* nominal2, float* prev1, float* prev2,
                                      float* opt_v, float* opt_w, float* stats, float* rank_partial,
                                      unsigned oob_count, unsigned nan_count, unsigned long long* tr,
-                                     float* host_cmd, unsigned host_seq)
+                                     float* host_cmd, unsigned host_seq, const PeerComm* pc = nullptr)
 {
     const int T = p.T, tid = threadIdx.x, B = blockDim.x;
     const int stride = partial_stride(T);
@@ -201,6 +201,37 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
             rank_partial[0] = M; rank_partial[1] = S; rank_partial[2] = __int_as_float(arg); rank_partial[3] = S2;
         }
         for (int col = tid; col < 2 * T; col += B) rank_partial[kPartialHeader + col] = s.acc[col];
+        return;
+    }
+
+    if (pc != nullptr && pc->world > 0) {
+        // ---- sample-sharded mode with peer memory: exchange the rank partials inside this launch
+        const int world = pc->world, me = pc->rank;
+        const unsigned seq = pc->seq;
+        const size_t slot = ((size_t)(seq & 1u) * world + me) * stride;
+        for (int r = 0; r < world; ++r) {                  // NVLink stores (plain local stores for r == me)
+            float* dst = pc->x[r] + slot;
+            if (tid == 0) { dst[0] = M; dst[1] = S; dst[2] = __int_as_float(arg); dst[3] = S2; }
+            for (int col = tid; col < 2 * T; col += B) dst[kPartialHeader + col] = s.acc[col];
+        }
+        // the barrier orders every thread's stores before the system-scope release of the flags below
+        __syncthreads();
+        if (tid < world) {
+            unsigned int* theirs = pc->f[tid] + (seq & 1u) * world + me;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
+            const unsigned int* mine = pc->f[me] + (seq & 1u) * world + tid;
+            unsigned got;
+            for (unsigned spin = 0;; ++spin) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+                if (got == seq) break;
+                __nanosleep(64);
+                if (spin > (1u << 24)) __trap();           // a missing rank must fail loudly, never hang the GPU
+            }
+        }
+        __syncthreads();
+        combine_and_finalize(p, st, pc->x[me] + (size_t)(seq & 1u) * world * stride, world, s, nominal1, nominal2,
+                             prev1, prev2, opt_v, opt_w, stats, nullptr, oob_count, nan_count, nullptr, host_cmd,
+                             host_seq, nullptr);
         return;
     }
 
@@ -403,7 +434,7 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
                          A.stats + (size_t)rover * kStatsStride,
                          A.rank_partial ? A.rank_partial + (size_t)rover * stride : nullptr, oob_count, nan_count,
                          (A.trace != nullptr && rover == 0) ? A.trace + (size_t)blockIdx.x * kTraceSlots : nullptr,
-                         (rover == 0) ? A.host_cmd : nullptr, A.host_seq);
+                         (rover == 0) ? A.host_cmd : nullptr, A.host_seq, (rover == 0) ? &A.peers : nullptr);
     if (tid == 0) {                                       // re-arm for the next launch
         trace_stamp(A, 6);
         A.counters[rover * kCounterStride + 0] = 0u;

@@ -17,6 +17,19 @@ constexpr int kMaxBlock = 256;        // threads per block upper bound
 constexpr int kStatsStride = 8;       // floats per rover in the stats buffer
 constexpr int kCounterStride = 4;     // uints per rover: {ticket, oob, nan, 0}
 
+// Peer exchange of the sample-sharded multi-GPU step (one process per GPU; buffers mapped with CUDA IPC).
+// Rank r owns x[r]: [2 parities][world][partial_stride(T)] floats and f[r]: [2][world] arrival flags.  The last block
+// of rank g's fused kernel stores its rank partial into slot g of EVERY rank's buffer over NVLink, releases one flag
+// per peer, waits for the world's flags in its own buffer and folds the partials in rank order: compute + exchange +
+// update in ONE launch, no collective library call and no second kernel.
+constexpr int kMaxRanks = 8;
+struct PeerComm {
+    float* x[kMaxRanks];
+    unsigned int* f[kMaxRanks];
+    int32_t rank, world;              // world == 0: no peer exchange
+    uint32_t seq;                     // step sequence number (parity = seq & 1 selects the buffer half)
+};
+
 struct FusedArgs {
     MppiParams p;
     MppiState state;                  // used when states == nullptr
@@ -41,6 +54,7 @@ struct FusedArgs {
     unsigned long long* trace;        // optional device [nblocks][16] %globaltimer stamps (profiling aid), or nullptr
     float* host_cmd;                  // optional mapped pinned host memory [4]: {v*, w*, sequence, 0} (mppi_step_host)
     uint32_t host_seq;                // sequence number stored with the command
+    PeerComm peers;                   // sample-sharded multi-GPU exchange (world == 0: off)
 };
 
 struct CombineArgs {

@@ -160,14 +160,31 @@ int mppi_step_batched(MppiHandle *h, const MppiState *states_dev, int32_t n_rove
 
 /* Sample-sharded multi-GPU mode (BASELINE config 3): this rank rolls out global samples
  * [k_begin, k_begin + params.K) and writes its softmax partial {M, S, argmin(int bits), A1[T], A2[T]}
- * (3 + 2T floats) to partial_dev instead of updating the nominal.  After the ranks exchange partials
+ * (4 + 2T floats) to partial_dev instead of updating the nominal.  After the ranks exchange partials
  * (one all-gather), mppi_combine_partials folds `n_parts` partials in rank order -- identically on every
  * rank -- and finishes the update (nominal, v*, w*). */
 int mppi_step_partial(MppiHandle *h, const MppiState *state, int32_t proj, const float *noise_dev,
                       uint64_t seed, uint64_t offset, uint32_t k_begin, float *partial_dev, void *stream);
 int mppi_combine_partials(MppiHandle *h, const MppiState *state, const float *partials_dev, int32_t n_parts,
                           void *stream);
-int mppi_partial_floats(int32_t T);   /* 3 + 2T */
+int mppi_partial_floats(int32_t T);   /* 4 + 2T */
+
+/* The same sharded step as ONE launch per rank, exchanging the rank partials over NVLink peer memory inside the
+ * fused kernel (no collective-library call, no second kernel).  One process per GPU on one NVSwitch node:
+ *   1. every rank: mppi_comm_export(h, world, handle)        -> 64-byte CUDA IPC handle of its exchange buffer
+ *   2. the ranks all-gather the handles (any host transport; sharding.py uses torch.distributed)
+ *   3. every rank: mppi_comm_connect(h, rank, world, handles)   with handles = world x 64 bytes, in rank order
+ *   4. per iteration, on every rank: mppi_step_sharded(...)  -- the last block of the launch stores the rank
+ *      partial into every peer, releases a flag per peer, waits (bounded; traps on a missing rank) for the world's
+ *      flags and folds the partials in rank order, so all ranks finish with the identical nominal and command.
+ * All ranks must call mppi_step_sharded the same number of times. */
+int mppi_comm_export(MppiHandle *h, int32_t world, unsigned char *ipc_handle_out /* [64] */);
+int mppi_comm_connect(MppiHandle *h, int32_t rank, int32_t world, const unsigned char *ipc_handles);
+int mppi_step_sharded(MppiHandle *h, const MppiState *state, int32_t proj, const float *noise_dev,
+                      uint64_t seed, uint64_t offset, uint32_t k_begin, void *stream);
+/* Same + the command (v*[0], w*[0]) delivered to cmd_host[2] as in mppi_step_host (zero-copy store, host poll). */
+int mppi_step_sharded_host(MppiHandle *h, const MppiState *state, int32_t proj, uint64_t seed, uint64_t offset,
+                           uint32_t k_begin, float *cmd_host, void *stream);
 
 /* Replaces launch 9 (MPPI_isaac.py:696-720): rollout of the optimal sequence (dim = 1) from `state`,
  * filling sim_traj / sim_heading. Lazy: only run() consumes element [0] (MPPI_isaac.py:769-772). */

@@ -216,3 +216,44 @@ def test_controller_run_closed_loop_reaches_a_near_goal():
     assert loops > 5 and d1 < 0.75 * d0, (loops, d0, d1)          # it moves toward the goal
     assert len(robot.x) == loops + 1 and len(robot.lin_vel) == loops
     ctl.close()
+
+
+def test_fused_peer_exchange_world1_equals_plain_step(oracle):
+    """The sample-sharded step with the exchange fused into the launch (mppi_step_sharded), world = 1: the rank
+    partial goes through the exchange buffer and the flag hand-shake and must reproduce mppi_step."""
+    import torch
+    from mppi_b200.sharding import SampleShardedStepper
+    K, T = 2048, 50
+    st = state_struct(default_state())
+    core, *_ = make_core(K, T, lambda_=50.0)
+    core.step(st, seed=3, offset=9)
+    torch.cuda.synchronize()
+    a = (core.optimal_u1.cpu().numpy().copy(), core.optimal_v.cpu().numpy().copy(), core.read_stats())
+    stepper = SampleShardedStepper(core, K, transport="p2p")
+    for _ in range(3):                                   # both buffer parities
+        core.set_nominal(np.zeros(T, np.float32), np.zeros(T, np.float32))
+        stepper.step(st, 3, 3, 9)
+        torch.cuda.synchronize()
+        b = (core.optimal_u1.cpu().numpy(), core.optimal_v.cpu().numpy(), core.read_stats())
+        assert a[2]["argmin"] == b[2]["argmin"] and a[2]["min_cost"] == b[2]["min_cost"]
+        assert close(b[0], a[0]) < 1e-6 and close(b[1], a[1]) < 1e-6
+    core.close()
+
+
+def test_fused_peer_exchange_across_gpus(tmp_path):
+    """Two (or more) processes, one GPU each, launched with torchrun: p2p and NCCL transports and the unsharded
+    controller agree.  Skipped on single-GPU boxes (tests/multi_gpu_check.py is the script it runs)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_gpu_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTI_GPU_CHECK_OK" in r.stdout

@@ -136,7 +136,7 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.05):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -258,9 +258,9 @@ def main():
 
     # warm-up
     timed_loop(max(3, args.warmup), 0, do_flush)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    barrier()
     t_wall0 = time.perf_counter()
     per_step_ms = timed_loop(args.steps, 1000, do_flush)
     barrier()
@@ -355,7 +355,9 @@ def main():
                         + ("inside the fused launch over NVLink peer memory (CUDA IPC), no collective call"
                            if args.exchange == "p2p" else "with one NCCL all-gather + combine kernel"))},
             "latency_us": {"p50": float(np.median(per_step_ms) * 1e3), "p99": float(np.percentile(per_step_ms, 99) * 1e3),
-                           "mean": float(per_step_ms.mean() * 1e3)},
+                           "mean": float(per_step_ms.mean() * 1e3), "max": float(per_step_ms.max() * 1e3),
+                           "argmax_step": int(per_step_ms.argmax()),
+                           "steps_over_2x_p50": int((per_step_ms > 2 * np.median(per_step_ms)).sum())},
             "warm_l2": {"ms_per_step": float(warm_ms.mean()), "p50_us": float(np.median(warm_ms) * 1e3),
                         "value": K_total * T / float(warm_ms.mean() * 1e-3)},
             "e2e": e2e,

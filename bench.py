@@ -325,7 +325,7 @@ def main():
             "bound": "hbm", "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": hbm_achieved / pk["hbm_gbs"],
             "traffic": counters.get("dram_bytes_per_launch"),
-            "kernel": "mppi_fused_pipe_kernel<3D, Philox>" if K <= 148 * 32 * 4 and args.variant != "mono"
+            "kernel": "mppi_fused_pipe_kernel<3D, Philox>" if K <= 148 * 32 * 2 and args.variant != "mono"
                       else "mppi_fused_kernel<3D, Philox>",
             "kernel_share_of_step": 1.0,
             "algorithmic_bytes_per_sample_step": GATHER_BYTES_PER_SAMPLE_STEP,

@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmppi_b200.so")
+LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(_HERE, "libmppi_b200.so")   # override: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 
 MPPI_OK = 0

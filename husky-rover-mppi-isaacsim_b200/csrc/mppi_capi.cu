@@ -91,7 +91,7 @@ static void pick_launch(const MppiParams& p, int* block, int* nblocks, bool* pip
 {
     const int K = p.K, T = p.T;
     const bool can_pipe = true;
-    *pipe = can_pipe && (p.variant == MPPI_VARIANT_PIPE || (p.variant == MPPI_VARIANT_AUTO && K <= 148 * 32 * 4));
+    *pipe = can_pipe && (p.variant == MPPI_VARIANT_PIPE || (p.variant == MPPI_VARIANT_AUTO && K <= 148 * 32 * 2));
     if (*pipe) { *block = 128; *nblocks = (K + 31) / 32; return; }
     int b;
     if (K <= 148 * 32 * 2) b = 32;

@@ -35,6 +35,44 @@ __device__ __forceinline__ void trace_stamp(const FusedArgs& A, int slot)
     if (A.trace != nullptr && blockIdx.y == 0) A.trace[(size_t)blockIdx.x * kTraceSlots + slot] = globaltimer_ns();
 }
 
+// ------------------------------------------------------------------ L2 warm-up of the reachable terrain window
+// Every sample starts at the robot, so all blocks gather from the same window of the DEM / costmap: the square of
+// half-side R = T dt v_max (+ wheel offset + one cell) around the start.  After an L2 flush the first block to touch
+// a line pays HBM latency on its dependent chain (that block then finishes last: +3 us of tail at C2).  Each block
+// prefetches a 1/nblocks share of the window's 128-byte lines into L2 while its pipeline fills (C2: 8 lines per
+// block; C5: 32).  Purely a hint: no data dependence, out-of-range rows / columns are clipped.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void prefetch_window(const float* base, int n, float half_width, float res, float cx, float cy,
+                                                float reach, int part, int nparts, int tid, int nthreads)
+{
+    // columns i = (x + hw) / res, rows j = (hw - y) / res  (projection_warp.py:39-40, critics_warp.py:245-248)
+    const float inv = 1.0f / res;
+    int i0 = (int)((cx - reach + half_width) * inv) - 1, i1 = (int)((cx + reach + half_width) * inv) + 2;
+    int j0 = (int)((half_width - cy - reach) * inv) - 1, j1 = (int)((half_width - cy + reach) * inv) + 2;
+    i0 = max(i0, 0); j0 = max(j0, 0); i1 = min(i1, n - 1); j1 = min(j1, n - 1);
+    if (i1 < i0 || j1 < j0) return;
+    const int lines_per_row = ((i1 - i0) >> 5) + 2;             // 32 floats per 128-byte line, unaligned start
+    const int total = (j1 - j0 + 1) * lines_per_row;
+    const int per_part = (total + nparts - 1) / nparts;
+    const int begin = part * per_part, end = min(begin + per_part, total);
+    for (int l = begin + tid; l < end; l += nthreads) {
+        const int row = j0 + l / lines_per_row, seg = l - (l / lines_per_row) * lines_per_row;
+        const int col = min(i0 + seg * 32, n - 1);
+        prefetch_l2(base + (size_t)row * n + col);
+    }
+}
+
+__device__ __forceinline__ void prefetch_terrain(const MppiParams& p, const MppiState& st, const MppiTerrain& tr,
+                                                 int part, int nparts, int tid, int nthreads)
+{
+    const float reach = p.dt * p.v_max * (float)p.T + p.wheel_offset;
+    prefetch_window(tr.dem, tr.grid_size, tr.half_width, tr.resolution, st.x, st.y, reach + tr.resolution, part,
+                    nparts, tid, nthreads);
+    prefetch_window(tr.costmap, tr.costmap_size, tr.half_width, tr.costmap_resolution, st.x, st.y, reach, part, nparts,
+                    tid, nthreads);
+}
+
 // ------------------------------------------------------------------ block-level helpers
 __device__ __forceinline__ void pair_min(float& c, int& k, float oc, int ok)
 {
@@ -471,6 +509,7 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
     float* nominal1 = A.nominal1 + (size_t)rover * T;
     float* nominal2 = A.nominal2 + (size_t)rover * T;
     for (int t = tid; t < T; t += B) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
+    prefetch_terrain(p, st, tr, blockIdx.x, A.nblocks, tid, B);
     __syncthreads();
 
     const int k_local = blockIdx.x * B + tid;
@@ -529,6 +568,10 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
 // roles share the other two.  Rings live in shared memory; chunks of kPipeChunk steps are handed over with
 // mbarriers (full/empty pairs), so the chain warp runs its dependent chain without ever issuing the other
 // roles' instructions.  Arithmetic per sample is unchanged (same device functions => same bits).
+#ifndef MPPI_CHAIN_UNROLL
+#define MPPI_CHAIN_UNROLL 4         // unroll factor of the chain warp's per-chunk loop (A/B knob)
+#endif
+constexpr int kChainUnroll = MPPI_CHAIN_UNROLL;
 constexpr int kPipeStages = 4;      // ring depth in chunks
 constexpr int kPipeChunk = 4;       // steps per chunk (even: noise comes in pairs of steps)
 constexpr int kNoiseWarps = 2;
@@ -576,7 +619,7 @@ __host__ __device__ inline size_t pipe_smem_offset_floats(int T, int nblocks)
 }
 
 template <int PROJ, bool INJECT>
-__global__ void __launch_bounds__(kPipeThreads)
+__global__ void __launch_bounds__(kPipeThreads, 1)
 mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
 {
     extern __shared__ __align__(16) float smem_raw[];
@@ -687,7 +730,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             const unsigned ph = (c / kPipeStages) & 1;
             mbar_wait(&ps.full_a[sg], ph);
             mbar_wait(&ps.empty_b[sg], ph ^ 1);
-#pragma unroll
+#pragma unroll kChainUnroll
             for (int i = 0; i < kPipeChunk; ++i) {
                 const int t = c * kPipeChunk + i;
                 if (t < T) {
@@ -727,7 +770,9 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         }
         ps.crit[1][lane] = slope;
     } else {
-        // ---- obstacle + near-goal path critic + last point
+        // ---- obstacle + near-goal path critic + last point.  This warp idles while the pipeline fills: it first
+        //      warms L2 with this block's share of the reachable terrain window.
+        prefetch_terrain(p, st, tr, blockIdx.x, A.nblocks, lane, 32);
         float obs = 0.0f, pf_near = 0.0f, lx = st.x, ly = st.y;
         for (int c = 0; c < nchunks; ++c) {
             const int sg = c % kPipeStages;

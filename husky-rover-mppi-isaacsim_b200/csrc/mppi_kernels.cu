@@ -482,8 +482,42 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
 }
 
 // ------------------------------------------------------------------ the fused kernel
+// All T steps of one sample (monolithic kernel).  Steps come in (even, odd) pairs: one Philox call feeds both, and
+// the odd step skips the wheel points (dead: the slope critic reads even steps only).
+template <int PROJ, bool INJECT, bool CLAMP>
+__device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiState& st, const Terr& ter,
+                                               const SampleConsts& sc, const NoiseKey& nk, const Smem& s, SampleAcc& a,
+                                               uint32_t kg, const float* eps1, const float* eps2)
+{
+    const int T = p.T;
+    const DumpPtrs nod = {};
+    for (int t = 0; t < T; t += 2) {
+        float e1a, e1b, e2a, e2b;
+        if (INJECT) {
+            e1a = eps1[t]; e2a = eps2[t];
+            e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
+            e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
+        } else {
+            noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
+        }
+        {
+            const float u1 = sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
+            const float u2 = sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
+            sample_step<PROJ, false, CLAMP, true>(p, st, ter, sc, a, t, u1, u2, nod, 0);
+        }
+        if (t + 1 < T) {
+            const float u1 = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
+            const float u2 = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
+            sample_step<PROJ, false, CLAMP, false>(p, st, ter, sc, a, t + 1, u1, u2, nod, 0);
+        }
+    }
+}
+
+#ifndef MPPI_MONO_MINBLOCKS
+#define MPPI_MONO_MINBLOCKS 2       // A/B knob: resident 256-thread blocks per SM the register allocation must allow
+#endif
 template <int PROJ, bool INJECT>
-__global__ void __launch_bounds__(kMaxBlock)
+__global__ void __launch_bounds__(kMaxBlock, MPPI_MONO_MINBLOCKS)
 mppi_fused_kernel(const __grid_constant__ FusedArgs A)
 {
     extern __shared__ float smem_raw[];
@@ -525,27 +559,10 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
     if (valid) {
         SampleAcc a;
         sample_init<PROJ>(st, ter, a);
-        const DumpPtrs nod = {};
-        for (int t = 0; t < T; t += 2) {
-            float e1a, e1b, e2a, e2b;
-            if (INJECT) {
-                e1a = eps1[t]; e2a = eps2[t];
-                e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
-                e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
-            } else {
-                noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
-            }
-            {
-                const float u1 = sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
-                const float u2 = sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
-                sample_step<PROJ, false>(p, st, ter, sc, a, t, u1, u2, nod, 0);
-            }
-            if (t + 1 < T) {
-                const float u1 = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
-                const float u2 = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
-                sample_step<PROJ, false>(p, st, ter, sc, a, t + 1, u1, u2, nod, 0);
-            }
-        }
+        if (terrain_window_safe(p, st, tr))
+            rollout_sample<PROJ, INJECT, false>(p, st, ter, sc, nk, s, a, kg, eps1, eps2);
+        else
+            rollout_sample<PROJ, INJECT, true>(p, st, ter, sc, nk, s, a, kg, eps1, eps2);
         cost = sample_cost(p, sc, a, nullptr);
         A.costs[(size_t)rover * K + k_local] = cost;
         my_oob = (unsigned)(a.oob + unit_violation(a.dev));
@@ -576,6 +593,7 @@ constexpr int kPipeStages = 4;      // ring depth in chunks
 constexpr int kPipeChunk = 4;       // steps per chunk (even: noise comes in pairs of steps)
 constexpr int kNoiseWarps = 2;
 constexpr int kPipeThreads = 192;
+template <bool B> struct FastTag { static constexpr bool value = B; };
 enum { ROLE_NOISE0 = 0, ROLE_NOISE1 = 1, ROLE_CHAIN = 2, ROLE_WHEELS = 3, ROLE_FILTER = 4, ROLE_OBST = 5 };
 
 struct PipeSmem {
@@ -662,6 +680,8 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     const int k_read = valid ? k_local : K - 1;                 // idle lanes shadow the last sample (results unused)
     const uint32_t kg = A.k_begin + (uint32_t)k_read;
     const int nchunks = (T + kPipeChunk - 1) / kPipeChunk;
+    // chunks that take the check-free path: full chunks of a rollout that provably stays inside the maps
+    const int nfast = terrain_window_safe(p, st, tr) ? T / kPipeChunk : 0;
     int oob = 0;
 
     if (role < kNoiseWarps) {
@@ -725,7 +745,9 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             prev = tangent(normal_on_grid(q, ter.res), prev);
         }
         if (lane == 0) trace_stamp(A, 2);
-        for (int c = 0; c < nchunks; ++c) {
+        // FAST: a full chunk whose cell indices need no clamping (terrain_window_safe) -> no per-step checks at all
+        auto chunk = [&](int c, auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
             const int sg = c % kPipeStages;
             const unsigned ph = (c / kPipeStages) & 1;
             mbar_wait(&ps.full_a[sg], ph);
@@ -733,10 +755,10 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
 #pragma unroll kChainUnroll
             for (int i = 0; i < kPipeChunk; ++i) {
                 const int t = c * kPipeChunk + i;
-                if (t < T) {
+                if (FAST || t < T) {
                     const float v = ps.ring_a[sg][i][0][lane];
                     const float sn = ps.ring_a[sg][i][1][lane], cs = ps.ring_a[sg][i][2][lane];
-                    role_chain<PROJ>(p, ter, x, y, prev, v, sn, cs, n, oob, dev);
+                    role_chain<PROJ, !FAST>(p, ter, x, y, prev, v, sn, cs, n, oob, dev);
                     float* o = &ps.ring_b[sg][i][0][lane];
                     o[0] = x; o[32] = y;
                     if ((i & 1) == 0) {                  // only even steps feed the wheel / slope role
@@ -747,46 +769,57 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             }
             mbar_arrive(&ps.empty_a[sg]);
             mbar_arrive(&ps.full_b[sg]);
-        }
+        };
+        int c = 0;
+        for (; c < nfast; ++c) chunk(c, FastTag<true>{});
+        for (; c < nchunks; ++c) chunk(c, FastTag<false>{});
         oob += unit_violation(dev);
         if (lane == 0) trace_stamp(A, 3);
     } else if (role == ROLE_WHEELS) {
         // ---- wheels + slope critic
         float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e;
         float slope = 0.0f;
-        for (int c = 0; c < nchunks; ++c) {
+        auto chunk = [&](int c, auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
             const int sg = c % kPipeStages;
             mbar_wait(&ps.full_b[sg], (c / kPipeStages) & 1);
 #pragma unroll
             for (int i = 0; i < kPipeChunk; i += 2) {                 // even steps only feed the critic
                 const int t = c * kPipeChunk + i;
-                if (t < T) {
+                if (FAST || t < T) {
                     const float* o = &ps.ring_b[sg][i][0][lane];
-                    role_wheels<PROJ>(p, ter, t, o[0], o[32], make_float3(o[64], o[96], o[128]),
-                                      make_float3(o[160], o[192], o[224]), lw_e, rw_e, slope, oob);
+                    role_wheels<PROJ, !FAST>(p, ter, t, o[0], o[32], make_float3(o[64], o[96], o[128]),
+                                             make_float3(o[160], o[192], o[224]), lw_e, rw_e, slope, oob);
                 }
             }
             mbar_arrive(&ps.empty_b[sg]);
-        }
+        };
+        int c = 0;
+        for (; c < nfast; ++c) chunk(c, FastTag<true>{});
+        for (; c < nchunks; ++c) chunk(c, FastTag<false>{});
         ps.crit[1][lane] = slope;
     } else {
         // ---- obstacle + near-goal path critic + last point.  This warp idles while the pipeline fills: it first
         //      warms L2 with this block's share of the reachable terrain window.
         prefetch_terrain(p, st, tr, blockIdx.x, A.nblocks, lane, 32);
         float obs = 0.0f, pf_near = 0.0f, lx = st.x, ly = st.y;
-        for (int c = 0; c < nchunks; ++c) {
+        auto chunk = [&](int c, auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
             const int sg = c % kPipeStages;
             mbar_wait(&ps.full_b[sg], (c / kPipeStages) & 1);
 #pragma unroll
             for (int i = 0; i < kPipeChunk; ++i) {
                 const int t = c * kPipeChunk + i;
-                if (t < T) {
+                if (FAST || t < T) {
                     lx = ps.ring_b[sg][i][0][lane]; ly = ps.ring_b[sg][i][1][lane];
-                    role_obstacle(p, st, ter, sc, t, lx, ly, pf_near, obs, oob);
+                    role_obstacle<!FAST>(p, st, ter, sc, t, lx, ly, pf_near, obs, oob);
                 }
             }
             mbar_arrive(&ps.empty_b[sg]);
-        }
+        };
+        int c = 0;
+        for (; c < nfast; ++c) chunk(c, FastTag<true>{});
+        for (; c < nchunks; ++c) chunk(c, FastTag<false>{});
         ps.crit[2][lane] = obs; ps.crit[3][lane] = pf_near; ps.crit[4][lane] = lx; ps.crit[5][lane] = ly;
     }
     ps.oob[role][lane] = oob;

@@ -192,3 +192,21 @@ def test_closed_loop_sequence_stays_bit_identical(oracle):
                            wheel_l=float(ref.opt_v[0] - ref.opt_w[0] * 0.6),
                            wheel_r=float(ref.opt_v[0] + ref.opt_w[0] * 0.6))
     g.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["mono", "pipe"])
+def test_rollouts_leaving_the_map_are_clamped_like_the_oracle(oracle, variant):
+    """Start 0.6 m from the map edge, heading out, wheels already spinning: most samples leave the DEM.  The
+    reference has no bounds checks (undefined behaviour); the core clamps and counts -- the kernels take their
+    clamped code path here (terrain_window_safe is false) and must still reproduce the oracle's clamped costs bit for
+    bit, cell indices included, and report the violations."""
+    K, T = 512, 40
+    dem, cm, hw = terrain("small")
+    st = default_state(x=hw - 0.6, y=-hw + 0.9, hx=1.0, hy=-0.3, goal_x=0.0, goal_y=0.0, wheel_l=1.8, wheel_r=1.8)
+    nom = (np.full(T, 0.9, np.float32), np.full(T, 0.9, np.float32))
+    ref, got, d, sim = run_both(oracle, K, T, "small", state=st, nominal=nom, variant=variant)
+    assert ref.oob_clamps > 0 and got["oob"] > 0 and got["nan"] == 0
+    for n in ("dem_ij", "lw_ij", "rw_ij", "cm_ij"):
+        assert np.array_equal(d[n], ref.dump[n]), f"{n} differs"
+    assert np.array_equal(got["cost"], ref.dump["cost"]) and got["argmin"] == ref.argmin
+    assert rel_err(got["nominal1"], ref.nominal1_f64) < RTOL

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--rovers", type=int, default=512, help="C4 only: rovers per GPU (4096 rovers / 8 GPUs)")
     ap.add_argument("--K", type=int, default=0, help="override the workload's samples per GPU (diagnostics)")
     ap.add_argument("--T", type=int, default=0, help="override the workload's horizon (diagnostics)")
     return ap.parse_args()
@@ -180,6 +181,125 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------------------ multi-rover batch (C4)
+def run_rover_batch(args):
+    """BASELINE config 4: independent controllers sharded by rover, no communication.  Each GPU runs
+    `--rovers` rovers (default 512 = 4096 / 8) x K = 1024 x T = 64 in ONE launch (grid.y = rover); every rover has
+    its own DEM / costmap memory, pose, goal, nominal and Philox stream."""
+    import torch
+    import torch.distributed as dist
+    from mppi_b200 import capi, synthetic as syn
+    from mppi_b200.core import Core, make_state
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = syn.WORKLOADS["C4"]
+    K, T, R = args.K or w.K, args.T or w.T, args.rovers
+    pool = 16                                        # distinct synthetic maps; every rover gets its OWN copy in HBM
+    rng = np.random.default_rng(7 + rank)
+    dem_pool = torch.stack([syn.crater_dem(w.grid_size, w.half_width, seed=57 + i, device=dev) for i in range(pool)])
+    cm_pool = torch.stack([torch.from_numpy(syn.rock_costmap(w.costmap_size, w.half_width, n_rocks=90, seed=99 + i))
+                           for i in range(pool)]).to(dev)
+    idx = torch.arange(R, device=dev) % pool
+    dems, cms = dem_pool[idx].contiguous(), cm_pool[idx].contiguous()
+    core = Core(K, T, device=local_rank, math=args.math, max_rovers=R)
+    core.set_terrain_batched(dems, w.half_width, cms)
+    half = w.half_width / 2
+    states = [make_state(float(rng.uniform(-half, half)), float(rng.uniform(-half, half)),
+                         (float(np.cos(a)), float(np.sin(a)), 0.0), goal_x=float(rng.uniform(-half, half)),
+                         goal_y=float(rng.uniform(-half, half)))
+              for a in rng.uniform(0, 2 * np.pi, R)]
+    states_host = torch.frombuffer(bytearray(bytes((capi.MppiState * R)(*states))), dtype=torch.uint8).pin_memory()
+    states_dev = states_host.to(dev)
+    cmd_host = torch.empty((R, 2), dtype=torch.float32).pin_memory()
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def timed(n, first):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for i in range(n):
+            if not args.no_flush:
+                flush_buf.fill_(i & 0xff)
+            evs[i][0].record()
+            core.step_batched(states_dev, R, capi.PROJ_3D, 42, first + i)
+            evs[i][1].record()
+        torch.cuda.synchronize(dev)
+        return np.array([a.elapsed_time(b) for a, b in evs])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    steps = min(args.steps, 100)
+    timed(max(3, min(args.warmup, 10)), 0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    per = timed(steps, 1000)
+    barrier()
+    clocks = sampler.stop()
+    total_ms = float(per.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms = total_ms / steps
+    # end to end: rover states from pinned host memory in, all commands back on the host, inside the timed region
+    e2e_t = []
+    for i in range(min(steps, 30)):
+        if not args.no_flush:
+            flush_buf.fill_(i & 0xff)
+            torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        states_dev.copy_(states_host, non_blocking=True)
+        core.step_batched(states_dev, R, capi.PROJ_3D, 42, 5000 + i)
+        cmd_host.copy_(core.stats[:R, 6:8], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_mean = float(np.mean(e2e_t))
+    if world > 1:
+        t = torch.tensor([e2e_mean], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_mean = float(t.item())
+    if rank == 0:
+        pk = peaks()
+        units = R * K * T
+        dur = ms * 1e-3
+        fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        line = {
+            "metric": "MPPI sample-steps/s", "value": units * world / dur, "unit": "sample-steps/s", "n_gpus": world,
+            "steps": steps, "warmup": max(3, min(args.warmup, 10)), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "rovers_per_gpu": R, "rovers_total": R * world, "K": K, "T": T,
+                       "dem": f"{w.grid_size}x{w.grid_size} f32 per rover ({pool} distinct maps, one copy per rover)",
+                       "costmap": f"{w.costmap_size}x{w.costmap_size} f32 per rover", "math": args.math,
+                       "l2": "flushed between timed iterations (256 MiB fill)" if not args.no_flush else "warm",
+                       "parallelism": f"rover-sharded x{world}, no communication"},
+            "latency_us": {"p50": float(np.median(per) * 1e3), "p99": float(np.percentile(per, 99) * 1e3)},
+            "rover_updates_per_s": R * world / dur,
+            "e2e": {"value": units * world / e2e_mean, "unit": "sample-steps/s", "h2d_bytes_per_step": R * STATE_BYTES,
+                    "d2h_bytes_per_step": R * CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6),
+                    "call": "pinned states H2D + mppi_step_batched + all (v*, w*) D2H + stream synchronise"},
+            "gpu_launches": steps,
+            "roofline": {"bound": "hbm", "achieved": GATHER_BYTES_PER_SAMPLE_STEP * units / dur / 1e9, "peak": pk["hbm_gbs"],
+                         "unit": "GB/s", "frac": GATHER_BYTES_PER_SAMPLE_STEP * units / dur / 1e9 / pk["hbm_gbs"],
+                         "traffic": None, "kernel": "mppi_fused_kernel<3D, Philox>, grid.y = rover",
+                         "fp32": {"achieved": FLOP_PER_SAMPLE_STEP * units / dur / 1e12, "unit": "TFLOP/s",
+                                  "peak": fp32_peak, "frac": FLOP_PER_SAMPLE_STEP * units / dur / 1e12 / fp32_peak}},
+            "clocks": clocks,
+            "stats_rover0": core.read_stats(0),
+        }
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 _REAL_STDOUT = None
 
@@ -203,6 +323,9 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.workload == "C4":
+        run_rover_batch(args)
         return
 
     import torch

@@ -87,18 +87,19 @@ extern "C" int mppi_default_params(MppiParams* p, int32_t K, int32_t T)
 
 // Variant + block size.  Small K is latency-bound: the warp-specialised kernel (32 samples per 4-warp CTA) wins
 // while the grid fits the machine a few times over; large K wants the monolithic kernel with full CTAs.
-static void pick_launch(const MppiParams& p, int* block, int* nblocks, bool* pipe)
+// What counts is the number of samples in flight in the launch: K per rover x rovers.
+static void pick_launch(const MppiParams& p, int n_rovers, int* block, int* nblocks, bool* pipe)
 {
-    const int K = p.K, T = p.T;
-    const bool can_pipe = true;
-    *pipe = can_pipe && (p.variant == MPPI_VARIANT_PIPE || (p.variant == MPPI_VARIANT_AUTO && K <= 148 * 32 * 2));
+    const int K = p.K;
+    const long long total = (long long)K * (n_rovers > 0 ? n_rovers : 1);
+    *pipe = (p.variant == MPPI_VARIANT_PIPE || (p.variant == MPPI_VARIANT_AUTO && total <= 148 * 32 * 2));
     if (*pipe) { *block = 128; *nblocks = (K + 31) / 32; return; }
     int b;
-    if (K <= 148 * 32 * 2) b = 32;
-    else if (K <= 148 * 64 * 8) b = 64;
+    if (total <= 148 * 32 * 2) b = 32;
+    else if (total <= 148 * 64 * 8) b = 64;
     else b = 128;
+    while (b > 32 && b / 2 >= K) b /= 2;                    // no block wider than one rover's samples need
     while ((K + b - 1) / b > 8192 && b < kMaxBlock) b *= 2;
-    (void)T;
     *block = b;
     *nblocks = (K + b - 1) / b;
 }
@@ -118,7 +119,7 @@ extern "C" int mppi_create(const MppiParams* params, int32_t device, int32_t max
     memset(h, 0, sizeof(*h));
     h->p = *params; h->device = device; h->max_rovers = max_rovers;
     h->K_cap = params->K; h->T_cap = params->T;
-    pick_launch(*params, &h->block, &h->nblocks, &h->pipe);
+    pick_launch(*params, 1, &h->block, &h->nblocks, &h->pipe);
     if ((size_t)h->nblocks > 8192) { delete h; return MPPI_ERR_UNSUPPORTED; }
     const size_t R = (size_t)max_rovers, T = (size_t)params->T, K = (size_t)params->K;
     const size_t stride = (size_t)partial_stride(params->T);
@@ -166,7 +167,7 @@ extern "C" int mppi_set_params(MppiHandle* h, const MppiParams* params)
 {
     if (!h || !params_ok(params) || params->K > h->K_cap || params->T > h->T_cap) return MPPI_ERR_INVALID_ARG;
     h->p = *params;
-    pick_launch(*params, &h->block, &h->nblocks, &h->pipe);
+    pick_launch(*params, 1, &h->block, &h->nblocks, &h->pipe);
     return MPPI_OK;
 }
 
@@ -228,6 +229,7 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
         return MPPI_ERR_NO_TERRAIN;
     }
     CK(cudaSetDevice(h->device));
+    pick_launch(h->p, n_rovers, &h->block, &h->nblocks, &h->pipe);
     FusedArgs a;
     memset(&a, 0, sizeof(a));
     a.p = h->p;

@@ -19,6 +19,7 @@ PROJ_3D = 3
 MATH_STRICT = 0
 MATH_FAST = 1
 VARIANT_AUTO, VARIANT_MONO, VARIANT_PIPE = 0, 1, 2
+INPUT_SKID_STEER, INPUT_UNICYCLE = 0, 1
 PARTIAL_HEADER = 4
 STATS_STRIDE = 8
 
@@ -36,7 +37,7 @@ class MppiParams(C.Structure):
         ("lethal_thresh", C.c_float), ("lethal_penalty", C.c_float),
         ("near_goal_cut", C.c_float), ("speed_eps", C.c_float), ("pf_eps", C.c_float),
         ("pf_near_gain", C.c_float), ("slope_eps", C.c_float), ("slope_gain", C.c_float),
-        ("horizon", C.c_float), ("target_speed", C.c_float),
+        ("horizon", C.c_float), ("target_speed", C.c_float), ("input_model", C.c_int32),
     ]
 
 
@@ -139,7 +140,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.mppi_abi_version() != 1:
+        if L.mppi_abi_version() != 2:
             raise MppiError("libmppi_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -107,7 +107,8 @@ static void pick_launch(const MppiParams& p, int n_rovers, int* block, int* nblo
 static bool params_ok(const MppiParams* p)
 {
     return p && p->K > 0 && p->T >= 2 && p->T <= 512 && p->lambda > 0.f && p->dt > 0.f &&
-           (p->math == MPPI_MATH_STRICT || p->math == MPPI_MATH_FAST) && p->variant >= 0 && p->variant <= 2;
+           (p->math == MPPI_MATH_STRICT || p->math == MPPI_MATH_FAST) && p->variant >= 0 && p->variant <= 2 &&
+           (p->input_model == MPPI_INPUT_SKID_STEER || p->input_model == MPPI_INPUT_UNICYCLE);
 }
 
 extern "C" int mppi_create(const MppiParams* params, int32_t device, int32_t max_rovers, MppiHandle** out)

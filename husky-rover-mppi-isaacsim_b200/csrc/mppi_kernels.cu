@@ -281,12 +281,32 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         for (int col = tid; col < 2 * T; col += B) {
             const float nv = fdiv(s.acc[col], rS);
             const float drive = nv * p.opt_k * oma;
+            s.acc[col] = nv;
             if (col < T) { prev1[col] = s.nom1[col]; nominal1[col] = nv; s.nom1[col] = drive; }
             else { prev2[col - T] = s.nom2[col - T]; nominal2[col - T] = nv; s.nom2[col - T] = drive; }
         }
     }
     __syncthreads();
     if (tr != nullptr && tid == 0) tr[14] = globaltimer_ns();
+
+    if (p.input_model == MPPI_INPUT_UNICYCLE) {
+        // velocity-space model: the weighted (v, w) sequence is the optimal velocity sequence (s.acc holds it)
+        for (int t = tid; t < T; t += B) {
+            const float v = s.acc[t], w = s.acc[T + t];
+            opt_v[t] = v; opt_w[t] = w;
+            if (t == 0) {
+                stats[6] = v; stats[7] = w;
+                if (host_cmd != nullptr)
+                    *reinterpret_cast<float4*>(host_cmd) = make_float4(v, w, __uint_as_float(host_seq), 0.0f);
+            }
+        }
+        if (tid == 0) {
+            stats[0] = M; stats[1] = __int_as_float(arg); stats[2] = S;
+            stats[3] = __uint_as_float(oob_count); stats[4] = __uint_as_float(nan_count);
+            stats[5] = fdiv(S * S, S2);
+        }
+        return;
+    }
 
     // 5. optimal sequence -> (v*, w*) with (opt_k, opt_a) (MPPI_isaac.py:672-692).  The two wheel recurrences
     //    l <- l a + drive_l[t], r <- r a + drive_r[t] are the only sequential part: one lane of warp 0 runs the left
@@ -351,6 +371,7 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
                                              unsigned my_oob, unsigned my_nan, float* nominal1, float* nominal2)
 {
     const MppiParams& p = A.p;
+    const UBounds ub = make_ubounds(p);
     const int T = p.T, K = p.K, B = blockDim.x, tid = threadIdx.x;
     const uint32_t kg = A.k_begin + (uint32_t)(blockIdx.x * spb + k_in_block);
     if (my_oob) atomicAdd(&A.counters[rover * kCounterStride + 1], my_oob);
@@ -414,11 +435,11 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
                     } else {
                         noise_pair(nk, A.k_begin + (uint32_t)kl, (uint32_t)pr, e1a, e1b, e2a, e2b);
                     }
-                    a1a += we * sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
-                    a2a += we * sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
+                    a1a += we * sample_u(s.nom1, t, T, st.sigma1, e1a, ub.lo1, ub.hi1);
+                    a2a += we * sample_u(s.nom2, t, T, st.sigma2, e2a, ub.lo2, ub.hi2);
                     if (t + 1 < T) {
-                        a1b += we * sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
-                        a2b += we * sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
+                        a1b += we * sample_u(s.nom1, t + 1, T, st.sigma1, e1b, ub.lo1, ub.hi1);
+                        a2b += we * sample_u(s.nom2, t + 1, T, st.sigma2, e2b, ub.lo2, ub.hi2);
                     }
                 }
             }
@@ -490,6 +511,7 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
                                                uint32_t kg, const float* eps1, const float* eps2)
 {
     const int T = p.T;
+    const UBounds ub = make_ubounds(p);
     const DumpPtrs nod = {};
     for (int t = 0; t < T; t += 2) {
         float e1a, e1b, e2a, e2b;
@@ -501,13 +523,13 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
             noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
         }
         {
-            const float u1 = sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
-            const float u2 = sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
+            const float u1 = sample_u(s.nom1, t, T, st.sigma1, e1a, ub.lo1, ub.hi1);
+            const float u2 = sample_u(s.nom2, t, T, st.sigma2, e2a, ub.lo2, ub.hi2);
             sample_step<PROJ, false, CLAMP, true>(p, st, ter, sc, a, t, u1, u2, nod, 0);
         }
         if (t + 1 < T) {
-            const float u1 = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
-            const float u2 = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
+            const float u1 = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, ub.lo1, ub.hi1);
+            const float u2 = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, ub.lo2, ub.hi2);
             sample_step<PROJ, false, CLAMP, false>(p, st, ter, sc, a, t + 1, u1, u2, nod, 0);
         }
     }
@@ -686,6 +708,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
 
     if (role < kNoiseWarps) {
         // ---- noise: eps -> u for chunks c = role, role + kNoiseWarps, ...
+        const UBounds ub = make_ubounds(p);
         const float* eps1 = INJECT ? A.noise + ((size_t)rover * 2 * K + k_read) * T : nullptr;
         const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
         for (int c = role; c < nchunks; c += kNoiseWarps) {
@@ -703,11 +726,11 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                     } else {
                         noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
                     }
-                    ps.ring_u[sg][i][0][lane] = sample_u(s.nom1, t, T, st.sigma1, e1a, p.u1_min, p.u1_max);
-                    ps.ring_u[sg][i][1][lane] = sample_u(s.nom2, t, T, st.sigma2, e2a, p.u2_min, p.u2_max);
+                    ps.ring_u[sg][i][0][lane] = sample_u(s.nom1, t, T, st.sigma1, e1a, ub.lo1, ub.hi1);
+                    ps.ring_u[sg][i][1][lane] = sample_u(s.nom2, t, T, st.sigma2, e2a, ub.lo2, ub.hi2);
                     if (t + 1 < T) {
-                        ps.ring_u[sg][i + 1][0][lane] = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, p.u1_min, p.u1_max);
-                        ps.ring_u[sg][i + 1][1][lane] = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, p.u2_min, p.u2_max);
+                        ps.ring_u[sg][i + 1][0][lane] = sample_u(s.nom1, t + 1, T, st.sigma1, e1b, ub.lo1, ub.hi1);
+                        ps.ring_u[sg][i + 1][1][lane] = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, ub.lo2, ub.hi2);
                     }
                 }
             }
@@ -871,6 +894,7 @@ __global__ void __launch_bounds__(128) mppi_dump_kernel(const __grid_constant__ 
     d.dem_ij = A.d.dem_ij; d.lw_ij = A.d.lw_ij; d.rw_ij = A.d.rw_ij; d.cm_ij = A.d.cm_ij;
     SampleAcc a;
     sample_init<PROJ>(A.state, ter, a);
+    const UBounds ub = make_ubounds(p);
     const float* eps1 = INJECT ? A.noise + (size_t)k * T : nullptr;
     const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
     for (int t = 0; t < T; t += 2) {
@@ -883,13 +907,13 @@ __global__ void __launch_bounds__(128) mppi_dump_kernel(const __grid_constant__ 
             noise_pair(nk, A.k_begin + (uint32_t)k, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
         }
         {
-            const float u1 = sample_u(A.nominal1, t, T, A.state.sigma1, e1a, p.u1_min, p.u1_max);
-            const float u2 = sample_u(A.nominal2, t, T, A.state.sigma2, e2a, p.u2_min, p.u2_max);
+            const float u1 = sample_u(A.nominal1, t, T, A.state.sigma1, e1a, ub.lo1, ub.hi1);
+            const float u2 = sample_u(A.nominal2, t, T, A.state.sigma2, e2a, ub.lo2, ub.hi2);
             sample_step<PROJ, true>(p, A.state, ter, sc, a, t, u1, u2, d, (size_t)k * T + t);
         }
         if (t + 1 < T) {
-            const float u1 = sample_u(A.nominal1, t + 1, T, A.state.sigma1, e1b, p.u1_min, p.u1_max);
-            const float u2 = sample_u(A.nominal2, t + 1, T, A.state.sigma2, e2b, p.u2_min, p.u2_max);
+            const float u1 = sample_u(A.nominal1, t + 1, T, A.state.sigma1, e1b, ub.lo1, ub.hi1);
+            const float u2 = sample_u(A.nominal2, t + 1, T, A.state.sigma2, e2b, ub.lo2, ub.hi2);
             sample_step<PROJ, true>(p, A.state, ter, sc, a, t + 1, u1, u2, d, (size_t)k * T + t + 1);
         }
     }

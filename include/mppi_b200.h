@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MPPI_B200_ABI_VERSION 1
+#define MPPI_B200_ABI_VERSION 2
 
 enum {
     MPPI_OK = 0,
@@ -47,6 +47,15 @@ enum { MPPI_MATH_STRICT = 0, MPPI_MATH_FAST = 1 };
  *        critics) handing stages over through shared-memory rings (latency regime, K of a few thousand). */
 enum { MPPI_VARIANT_AUTO = 0, MPPI_VARIANT_MONO = 1, MPPI_VARIANT_PIPE = 2 };
 
+/* What is sampled.
+ *  SKID_STEER: wheel inputs (u1, u2) perturbed around the nominal, then the first-order wheel filter -> (v, w):
+ *              _generate_inputs_kernel + _convert_inputs_to_velocities (sampling_warp.py:54-138), what MPPI_isaac.py runs.
+ *  UNICYCLE:   (v, w) perturbed directly around the previous optimal velocity sequence, clamped to the velocity
+ *              limits, no filter: _generate_velocities_kernel (sampling_warp.py:10-48; driven by old_files/run_mppi.py).
+ *              The nominal / optimal_u1,u2 buffers then hold (v, w) and optimal_v/w are copies of them;
+ *              MppiState.sigma1 / sigma2 are std_dev_linear / std_dev_angular. */
+enum { MPPI_INPUT_SKID_STEER = 0, MPPI_INPUT_UNICYCLE = 1 };
+
 /* Every tunable / literal of the reference hot path. Defaults via mppi_default_params. */
 typedef struct MppiParams {
     int32_t K;              /* number_of_trajectories                       config.yaml:7   */
@@ -71,6 +80,7 @@ typedef struct MppiParams {
     float slope_gain;       /* 5.0   critics_warp.py:209-210 */
     float horizon;          /* dt*v_max*T  MPPI_isaac.py:440 (host double -> float) */
     float target_speed;     /* v_max_linear MPPI_isaac.py:619 */
+    int32_t input_model;    /* MPPI_INPUT_* */
 } MppiParams;
 
 /* Terrain = DEM `Z_wp` + obstacle `costmap_wp` (MPPI_isaac.py:463-464), borrowed device pointers. */

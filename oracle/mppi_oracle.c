@@ -394,12 +394,21 @@ static void *worker_main(void *arg)
         /* A.1 sampling_warp.py:54-92 (receding-horizon shift folded in) */
         for (int t = 0; t < T; ++t) {
             int src = (t != T - 1) ? t + 1 : t;
-            u1[o + t] = clampf(nom1[src] + st->sigma1 * eps1[o + t], p->u1_min, p->u1_max);
-            u2[o + t] = clampf(nom2[src] + st->sigma2 * eps2[o + t], p->u2_min, p->u2_max);
+            if (p->input_model == 1) {   /* velocity space, sampling_warp.py:10-48 */
+                u1[o + t] = clampf(nom1[src] + st->sigma1 * eps1[o + t], p->v_min, p->v_max);
+                u2[o + t] = clampf(nom2[src] + st->sigma2 * eps2[o + t], p->w_min, p->w_max);
+            } else {
+                u1[o + t] = clampf(nom1[src] + st->sigma1 * eps1[o + t], p->u1_min, p->u1_max);
+                u2[o + t] = clampf(nom2[src] + st->sigma2 * eps2[o + t], p->u2_min, p->u2_max);
+            }
         }
         float *v = dump->v ? dump->v + o : vloc;
         float *w = dump->w ? dump->w + o : vloc + T;
-        wheel_filter(p, st, p->filt_k, p->filt_a, T, u1 + o, u2 + o, v, w);
+        if (p->input_model == 1) {
+            for (int t = 0; t < T; ++t) { v[t] = u1[o + t]; w[t] = u2[o + t]; }
+        } else {
+            wheel_filter(p, st, p->filt_k, p->filt_a, T, u1 + o, u2 + o, v, w);
+        }
         float *traj = dump->traj ? dump->traj + 3 * o : tloc;
         float *hd = dump->heading ? dump->heading + 3 * o : tloc + 3 * T;
         float *lw = dump->lw ? dump->lw + 3 * o : tloc + 6 * T;
@@ -488,7 +497,11 @@ int oracle_mppi_step(const OrParams *p, const OrTerrain *ter, const OrState *st,
     out->min_cost = m; out->argmin = arg; out->weights_sum = S;
 
     /* A.9: optimal sequence -> (v*, w*) with (k, a) = (opt_k, opt_a)  MPPI_isaac.py:672-692 */
-    wheel_filter(p, st, p->opt_k, p->opt_a, T, out->nominal1, out->nominal2, out->opt_v, out->opt_w);
+    if (p->input_model == 1) {   /* the weighted (v, w) sequence IS the optimal velocity sequence (old_files/run_mppi.py:228-245) */
+        for (int t = 0; t < T; ++t) { out->opt_v[t] = out->nominal1[t]; out->opt_w[t] = out->nominal2[t]; }
+    } else {
+        wheel_filter(p, st, p->opt_k, p->opt_a, T, out->nominal1, out->nominal2, out->opt_v, out->opt_w);
+    }
     /* optimal-trajectory rollout, dim = 1  MPPI_isaac.py:696-720 (always the 3-D kernel) */
     if (out->sim_traj && out->sim_heading) {
         OrParams p3 = *p; p3.proj = 3;

@@ -44,6 +44,9 @@ typedef struct OrParams {
     float slope_gain;     /* 5.0 critics_warp.py:209-210 */
     float horizon;        /* dt*v_max*T MPPI_isaac.py:440 (host float64 -> fp32) */
     float target_speed;   /* v_max_linear MPPI_isaac.py:619 */
+    int32_t input_model;  /* 0: wheel inputs u1,u2 + first-order filter (_generate_inputs_kernel sampling_warp.py:54-92,
+                             _convert_inputs_to_velocities :96-138); 1: velocity space (v, w) sampled directly
+                             (_generate_velocities_kernel sampling_warp.py:10-48), no filter */
 } OrParams;
 
 typedef struct OrTerrain {

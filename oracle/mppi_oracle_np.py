@@ -32,9 +32,10 @@ DEFAULTS = dict(
 class P:
     """Parameter bag with every field as np.float32 (ints stay ints)."""
 
-    def __init__(self, K, T, proj=3, **kw):
+    def __init__(self, K, T, proj=3, input_model=0, **kw):
         d = dict(DEFAULTS)
         d.update(kw)
+        self.input_model = int(input_model)      # 0 wheel inputs + filter, 1 velocity space (sampling_warp.py:10-48)
         d.setdefault("horizon", d["dt"] * d["v_max"] * T)         # MPPI_isaac.py:440
         d.setdefault("target_speed", d["v_max"])                  # MPPI_isaac.py:619
         self.K, self.T, self.proj = int(K), int(T), int(proj)
@@ -50,8 +51,10 @@ def sample_inputs(p, nom1, nom2, s1, s2, eps1, eps2):
     """sampling_warp.py:54-92: u[k,t] = clamp(nom[t+1] + sigma*eps) (last step reuses nom[T-1])."""
     T = p.T
     src = np.minimum(np.arange(T) + 1, T - 1)
-    u1 = clamp(_F(nom1)[src][None, :] + f32(s1) * _F(eps1), p.u1_min, p.u1_max)
-    u2 = clamp(_F(nom2)[src][None, :] + f32(s2) * _F(eps2), p.u2_min, p.u2_max)
+    lo1, hi1, lo2, hi2 = ((p.v_min, p.v_max, p.w_min, p.w_max) if getattr(p, "input_model", 0) == 1
+                          else (p.u1_min, p.u1_max, p.u2_min, p.u2_max))
+    u1 = clamp(_F(nom1)[src][None, :] + f32(s1) * _F(eps1), lo1, hi1)
+    u2 = clamp(_F(nom2)[src][None, :] + f32(s2) * _F(eps2), lo2, hi2)
     return _F(u1), _F(u2)
 
 
@@ -288,7 +291,10 @@ def mppi_step(p: P, dem, half_width, costmap, state: dict, nom1, nom2, eps1, eps
     ter = Terrain(dem, half_width, costmap)
     st = {k: f32(v) for k, v in state.items()}
     u1, u2 = sample_inputs(p, nom1, nom2, st["sigma1"], st["sigma2"], eps1, eps2)
-    v, w = inputs_to_velocities(p, u1, u2, st["wheel_l"], st["wheel_r"], p.filt_k, p.filt_a)
+    if p.input_model == 1:
+        v, w = u1, u2                                             # velocity-space samples are (v, w) themselves
+    else:
+        v, w = inputs_to_velocities(p, u1, u2, st["wheel_l"], st["wheel_r"], p.filt_k, p.filt_a)
     h0 = np.array([st["hx"], st["hy"], st["hz"]], np.float32)
     ro = rollout(p, ter, st["x"], st["y"], h0, v, w)
     c_path = path_follow(p, st["x"], st["y"], st["goal_x"], st["goal_y"], ro["traj"])
@@ -313,7 +319,10 @@ def mppi_step(p: P, dem, half_width, costmap, state: dict, nom1, nom2, eps1, eps
     for k in nz:                                                  # zero weights add exactly +0
         n1 = n1 + wts[k] * u1[k] / S
         n2 = n2 + wts[k] * u2[k] / S
-    ov, ow = inputs_to_velocities(p, n1[None, :], n2[None, :], st["wheel_l"], st["wheel_r"], p.opt_k, p.opt_a)
+    if p.input_model == 1:
+        ov, ow = n1[None, :].copy(), n2[None, :].copy()
+    else:
+        ov, ow = inputs_to_velocities(p, n1[None, :], n2[None, :], st["wheel_l"], st["wheel_r"], p.opt_k, p.opt_a)
     p3 = P(1, p.T, proj=3)
     p3.__dict__.update({k: v_ for k, v_ in p.__dict__.items() if k not in ("K", "proj")})
     p3.K, p3.proj = 1, 3

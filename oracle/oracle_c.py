@@ -32,7 +32,7 @@ class OrParams(C.Structure):
         ("lethal_thresh", C.c_float), ("lethal_penalty", C.c_float),
         ("near_goal_cut", C.c_float), ("speed_eps", C.c_float), ("pf_eps", C.c_float),
         ("pf_near_gain", C.c_float), ("slope_eps", C.c_float), ("slope_gain", C.c_float),
-        ("horizon", C.c_float), ("target_speed", C.c_float),
+        ("horizon", C.c_float), ("target_speed", C.c_float), ("input_model", C.c_int32),
     ]
 
 

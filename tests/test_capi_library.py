@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound(capi):
 
 def test_abi_version_and_strerror(capi):
     lib = capi.lib()
-    assert lib.mppi_abi_version() == 1
+    assert lib.mppi_abi_version() == 2
     assert lib.mppi_strerror(0) == b"ok"
     assert b"invalid" in lib.mppi_strerror(-1)
     assert b"terrain" in lib.mppi_strerror(-3)
@@ -53,7 +53,7 @@ def test_default_params_are_the_reference_values(capi):
 
 
 def test_struct_layouts_match_the_header(capi):
-    assert C.sizeof(capi.MppiParams) == 4 * 4 + 30 * 4
+    assert C.sizeof(capi.MppiParams) == 4 * 4 + 30 * 4 + 4      # + input_model (ABI version 2)
     assert C.sizeof(capi.MppiState) == 48
     assert C.sizeof(capi.MppiTerrain) == 40
     assert C.sizeof(capi.MppiOutputs) == 8 * 8

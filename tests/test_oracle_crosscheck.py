@@ -157,3 +157,21 @@ def test_combine_partials_is_invariant_to_the_split(oracle):
         assert arg == c.argmin and m == c.min_cost
         np.testing.assert_allclose(n1, c.nominal1_f64, rtol=2e-6, atol=1e-7)
         np.testing.assert_allclose(n2, c.nominal2_f64, rtol=2e-6, atol=1e-7)
+
+
+def test_velocity_space_input_model_c_vs_numpy(oracle):
+    """input_model = 1 (unicycle: _generate_velocities_kernel, sampling_warp.py:10-48): (v, w) are sampled directly
+    around the previous optimal velocity sequence and clamped to the velocity limits; no wheel filter anywhere."""
+    K, T = 192, 40
+    nom = (np.full(T, 0.8, f32), np.linspace(-0.3, 0.3, T).astype(f32))
+    st = default_state(sigma1=0.3, sigma2=0.2, wheel_l=0.7, wheel_r=0.1)       # wheel speeds must be ignored
+    c, n = both(oracle, K, T, "C1", nominal=nom, seed=4, state=st, input_model=1, lam=500.0)
+    e1, e2 = normals(K, T, 4)
+    src = np.minimum(np.arange(T) + 1, T - 1)
+    v_expect = np.clip(nom[0][src][None, :] + f32(0.3) * e1, f32(0.0), f32(2.0)).astype(f32)
+    assert np.array_equal(c.dump["v"], v_expect) and np.array_equal(c.dump["u1"], c.dump["v"])
+    assert np.array_equal(c.dump["w"], n["w"]) and np.array_equal(c.dump["u2"], c.dump["w"])
+    assert c.argmin == n["argmin"]
+    np.testing.assert_allclose(c.dump["cost"], n["cost"], rtol=2e-5)
+    np.testing.assert_allclose(c.nominal1, n["nominal1"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(c.opt_v, c.nominal1) and np.array_equal(c.opt_w, c.nominal2)

@@ -43,6 +43,7 @@ def parse():
                     help="multi-GPU exchange of the softmax partials: fused peer-memory stores or NCCL all-gather")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-closed-loop", action="store_true", help="skip the closed-loop (run()) measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--rovers", type=int, default=512, help="C4 only: rovers per GPU (4096 rovers / 8 GPUs)")
     ap.add_argument("--K", type=int, default=0, help="override the workload's samples per GPU (diagnostics)")
@@ -434,6 +435,39 @@ def main():
         e2e = {"value": K_total * T / float(t.item()), "unit": "sample-steps/s", "h2d_bytes_per_step": STATE_BYTES,
                "d2h_bytes_per_step": CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6)}
 
+    # f2: the offline closed loop of MPPI_Controller.run resident on the device (one launch per iteration, plant step
+    # and feedback logic inside the kernel) vs the same loop driven from the host with a read-back per iteration.
+    closed_loop = None
+    if n_gpus == 1 and not args.no_closed_loop:
+        import copy
+        n_it = 500
+        st_d = copy.copy(state)
+        core.set_nominal(np.zeros(T, np.float32), np.zeros(T, np.float32))
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        done, reached, _ = core.run_closed_loop(st_d, n_it, capi.PROJ_3D, seed, 50000, want_log=True)
+        t_dev = time.perf_counter() - t0
+        st_h = copy.copy(state)
+        core.set_nominal(np.zeros(T, np.float32), np.zeros(T, np.float32))
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(n_it):
+            v0, w0 = core.step_host(st_h, capi.PROJ_3D, seed, 50000 + i)
+            core.sim_rollout(st_h)
+            pose = torch.cat([core.sim_traj[0], core.sim_heading[0]]).cpu().numpy()
+            hv = pose[3:6] / np.linalg.norm(pose[3:6])
+            st_h.x, st_h.y, st_h.hx, st_h.hy, st_h.hz = float(pose[0]), float(pose[1]), float(hv[0]), float(hv[1]), float(hv[2])
+            w2 = np.float32(w0) * np.float32(w0)
+            st_h.sigma1, st_h.sigma2 = float(max(np.float32(0.4), np.float32(0.4) - w2)), float(max(np.float32(0.4), np.float32(0.4) + w2))
+            st_h.wheel_l = float(np.float32(v0) - np.float32(w0) * np.float32(1.2) / np.float32(2))
+            st_h.wheel_r = float(np.float32(v0) + np.float32(w0) * np.float32(1.2) / np.float32(2))
+        t_host = time.perf_counter() - t0
+        closed_loop = {"iterations": int(done), "device_resident_us_per_iteration": t_dev / max(1, done) * 1e6,
+                       "host_driven_us_per_iteration": t_host / n_it * 1e6,
+                       "reference_published_us_per_loop": 3000.0,
+                       "note": "MPPI_Controller.run (MPPI_isaac.py:755-805): plant = the controller's own model; "
+                               "reference figure: 'work summarise':71 (K=1000, T=100, unspecified GPU)"}
+
     if rank == 0:
         pk = peaks()
         # Contract object: algorithmic gather bytes against the MEASURED HBM peak.  The path is served from L1/L2
@@ -486,6 +520,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": args.steps * (1 if (n_gpus == 1 or args.exchange == "p2p") else 2),
             "roofline": roofline,
+            "closed_loop": closed_loop,
             "clocks": clocks,
             "wall_s": wall_s,
             "stats": core.read_stats(),

@@ -91,6 +91,9 @@ SYMBOLS = {
                                          C.c_void_p, C.c_void_p]),
     "mppi_step_sharded": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64,
                                     C.c_uint32, C.c_void_p]),
+    "mppi_run_closed_loop": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64,
+                                       C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
     "mppi_sim_rollout": (C.c_int, [_H, C.POINTER(MppiState), C.c_void_p]),
     "mppi_debug_dump": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32,
                                   C.POINTER(MppiDebugDump), C.c_void_p]),

@@ -228,7 +228,7 @@ class MPPI_Controller:
 
     def _state(self) -> capi.MppiState:
         r = self.robot
-        hv = np.asarray(r.heading_vector, dtype=np.float64)
+        hv = np.asarray(r.heading_vector)                                # dtype kept: run() stores a float32 array
         hv = hv / np.linalg.norm(hv)                                     # MPPI_isaac.py:493
         return capi.MppiState(float(r.x[-1]), float(r.y[-1]), float(hv[0]), float(hv[1]), float(hv[2]),
                               float(r.left_wheel_speed), float(r.right_wheel_speed),
@@ -240,8 +240,9 @@ class MPPI_Controller:
         steps instead of the Philox stream (None restores production mode)."""
         if eps is not None:
             K, T = self.number_of_trajectories, self.number_of_iterations
-            if tuple(eps.shape) != (2, K, T) or eps.dtype != torch.float32 or not eps.is_cuda:
-                raise ValueError("eps must be a float32 CUDA tensor of shape [2, K, T]")
+            if tuple(eps.shape[-3:]) != (2, K, T) or eps.dim() not in (3, 4) or eps.dtype != torch.float32 \
+                    or not eps.is_cuda:
+                raise ValueError("eps must be a float32 CUDA tensor of shape [2, K, T] ([n, 2, K, T] for device_loop)")
             eps = eps.contiguous()
         self._injected_noise = eps
 
@@ -319,18 +320,25 @@ class MPPI_Controller:
         return DeviceArray(self.debug_dump(("traj",))["traj"].reshape(K * T, 3))
 
     # ------------------------------------------------------------------ offline closed loop
-    def run(self, proj="3d", max_loops: int = 3500):
-        """Closed loop with the controller's own model as the plant, MPPI_isaac.py:755-805."""
+    def run(self, proj="3d", max_loops: int = 3500, device_loop: bool = False):
+        """Closed loop with the controller's own model as the plant, MPPI_isaac.py:755-805.
+
+        device_loop=False walks the reference's host loop (one MPPI_step + read-backs per iteration).
+        device_loop=True runs the same loop resident on the device (mppi_run_closed_loop: one fused launch per
+        iteration, pose / sigma / wheel-speed feedback and the goal test inside the kernel) and then fills the
+        robot's history exactly as the host loop would have."""
         self.warp_setup()
+        if device_loop:
+            return self._run_on_device(proj, max_loops)
         while (abs(self.robot.x[-1] - self.goal_x) > 0.5 or abs(self.robot.y[-1] - self.goal_y) > 0.5) \
                 and self.loop < max_loops:
             self.reset("controller")
             self.MPPI_step(proj=proj)
             traj0 = self.trajectories_sim.numpy()[0]
             head0 = self.heading_vectors_sim.numpy()[0]
-            self.robot.update_position(float(traj0[0]), float(traj0[1]), float(traj0[2]), head0.astype(np.float64))
-            lin_vel = float(self.optimal_lin_vel_wp.numpy()[0])
-            ang_vel = float(self.optimal_ang_vel_wp.numpy()[0])
+            self.robot.update_position(traj0[0], traj0[1], traj0[2], head0)
+            lin_vel = self.optimal_lin_vel_wp.numpy()[0]
+            ang_vel = self.optimal_ang_vel_wp.numpy()[0]
             self.std_dev_u1 = np.maximum(0.4, 0.4 - ang_vel * ang_vel)          # MPPI_isaac.py:777-778
             self.std_dev_u2 = np.maximum(0.4, 0.4 + ang_vel * ang_vel)
             self.robot.lin_vel.append(lin_vel)
@@ -338,6 +346,38 @@ class MPPI_Controller:
             self.robot.left_wheel_speed = lin_vel - ang_vel * self.robot.radius / 2
             self.robot.right_wheel_speed = lin_vel + ang_vel * self.robot.radius / 2
             self.loop += 1
+        return self.loop
+
+    def _run_on_device(self, proj, max_loops):
+        if self._terrain_dirty:
+            self._push_terrain()
+        n = max_loops - self.loop
+        if n <= 0 or not (abs(self.robot.x[-1] - self.goal_x) > 0.5 or abs(self.robot.y[-1] - self.goal_y) > 0.5):
+            return self.loop
+        pj = capi.PROJ_3D if proj == "3d" else capi.PROJ_2D
+        st = self._state()
+        log = np.zeros((n, 8), np.float32)
+        done, reached = C.c_int32(0), C.c_int32(0)
+        noise = self._injected_noise
+        if noise is not None and noise.dim() == 3:
+            raise ValueError("device_loop needs injected noise of shape [iterations, 2, K, T]")
+        self._stream = torch.cuda.current_stream(self.device).cuda_stream
+        capi.check(self._lib.mppi_run_closed_loop(self._handle, C.byref(st), pj,
+                                                  noise.data_ptr() if noise is not None else None, self.seed,
+                                                  self._step_count, n, 0.5, 0.4, 1.0, log.ctypes.data,
+                                                  C.byref(done), C.byref(reached), self._stream),
+                   "mppi_run_closed_loop")
+        k = int(done.value)
+        for row in log[:k]:
+            self.robot.update_position(row[0], row[1], row[2], row[3:6].copy())
+            self.robot.lin_vel.append(row[6])
+            self.robot.ang_vel.append(row[7])
+        self.std_dev_u1, self.std_dev_u2 = np.float32(st.sigma1), np.float32(st.sigma2)
+        self.robot.left_wheel_speed, self.robot.right_wheel_speed = np.float32(st.wheel_l), np.float32(st.wheel_r)
+        self._last_state, self._last_proj = st, pj
+        self._step_count += k
+        self.loop += k
+        self._sim_stale = True
         return self.loop
 
     def close(self):

@@ -139,6 +139,20 @@ class Core:
                                                  self._stream(stream)), "mppi_step_sharded_host")
         return self._cmd[0], self._cmd[1]
 
+    def run_closed_loop(self, state: capi.MppiState, max_iters: int, proj: int = capi.PROJ_3D, seed: int = 0,
+                        offset0: int = 0, goal_tol: float = 0.5, sigma_base: float = 0.4, sigma_gain: float = 1.0,
+                        noise: Optional[torch.Tensor] = None, want_log: bool = True, stream=None):
+        """Device-resident closed loop (mppi_run_closed_loop).  Returns (iterations done, goal reached, log[k, 8]);
+        `state` is updated in place to the state after the last iteration."""
+        log = np.zeros((max_iters, 8), np.float32) if want_log else None
+        done, reached = C.c_int32(0), C.c_int32(0)
+        capi.check(self.L.mppi_run_closed_loop(self.h, C.byref(state), proj,
+                                               noise.data_ptr() if noise is not None else None, seed, offset0,
+                                               max_iters, goal_tol, sigma_base, sigma_gain,
+                                               log.ctypes.data if want_log else None, C.byref(done),
+                                               C.byref(reached), self._stream(stream)), "mppi_run_closed_loop")
+        return int(done.value), bool(reached.value), (log[:done.value] if want_log else None)
+
     def sim_rollout(self, state, stream=None):
         capi.check(self.L.mppi_sim_rollout(self.h, C.byref(state), self._stream(stream)), "mppi_sim_rollout")
 

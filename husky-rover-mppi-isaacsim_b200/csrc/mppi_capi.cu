@@ -35,6 +35,11 @@ struct MppiHandle {
     void* comm_local;            // this rank's exchange allocation: [2][world][stride] floats + [2][world] flags
     void* comm_peer[kMaxRanks];  // peers' allocations opened with CUDA IPC (nullptr for this rank)
     PeerComm peers;
+    // device-resident closed loop (mppi_run_closed_loop)
+    MppiState* loop_state;       // device
+    int32_t* loop_ctl;           // device {iterations done, goal reached}
+    float* loop_log;             // device [loop_log_cap][8]
+    int32_t loop_log_cap;
 };
 
 static thread_local char g_cuda_err[256];
@@ -156,6 +161,9 @@ extern "C" int mppi_destroy(MppiHandle* h)
     for (float* b : bufs) if (b) cudaFree(b);
     for (int r = 0; r < kMaxRanks; ++r) if (h->comm_peer[r]) cudaIpcCloseMemHandle(h->comm_peer[r]);
     if (h->comm_local) cudaFree(h->comm_local);
+    if (h->loop_state) cudaFree(h->loop_state);
+    if (h->loop_ctl) cudaFree(h->loop_ctl);
+    if (h->loop_log) cudaFree(h->loop_log);
     if (h->counters) cudaFree(h->counters);
     if (h->cmd_pinned) cudaFreeHost(h->cmd_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -220,10 +228,10 @@ extern "C" int mppi_get_nominal(MppiHandle* h, float* u1, float* u2, int32_t n_r
 
 static int do_step(MppiHandle* h, const MppiState* state, const MppiState* states_dev, int n_rovers, int proj,
                    const float* noise, uint64_t seed, uint64_t offset, uint32_t k_begin, float* rank_partial,
-                   cudaStream_t s, bool to_host = false, bool sharded = false)
+                   cudaStream_t s, bool to_host = false, bool sharded = false, const LoopCtl* loop = nullptr)
 {
     if (!h || (proj != MPPI_PROJ_2D && proj != MPPI_PROJ_3D)) return MPPI_ERR_INVALID_ARG;
-    if (!state && !states_dev) return MPPI_ERR_INVALID_ARG;
+    if (!state && !states_dev && !loop) return MPPI_ERR_INVALID_ARG;
     if (states_dev) {
         if (!h->terrains_dev || n_rovers > h->n_terrains) return MPPI_ERR_NO_TERRAIN;
     } else if (!h->has_terrain) {
@@ -247,6 +255,7 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     a.trace = h->trace;
     if (to_host) { a.host_cmd = h->cmd_pinned_dev; a.host_seq = ++h->host_seq; }
     if (sharded) { a.peers = h->peers; a.peers.seq = ++h->peers.seq; }
+    if (loop) a.loop = *loop;
     if (h->timing) CK(cudaEventRecord(h->ev0, s));
     cudaError_t e;
     if (h->pipe)
@@ -390,6 +399,58 @@ extern "C" int mppi_step_sharded_host(MppiHandle* h, const MppiState* state, int
     int rc = do_step(h, state, nullptr, 1, proj, nullptr, seed, offset, k_begin, nullptr, s, true, true);
     if (rc != MPPI_OK) return rc;
     return wait_host_command(h, cmd_host, s);
+}
+
+// ---------------------------------------------------------------- device-resident closed loop
+extern "C" int mppi_run_closed_loop(MppiHandle* h, MppiState* state_inout, int32_t proj, const float* noise_dev,
+                                    uint64_t seed, uint64_t offset0, int32_t max_iters, float goal_tol,
+                                    float sigma_base, float sigma_gain, float* log_host, int32_t* iters_done,
+                                    int32_t* goal_reached, void* stream)
+{
+    if (!h || !state_inout || max_iters < 1 || (proj != MPPI_PROJ_2D && proj != MPPI_PROJ_3D)) return MPPI_ERR_INVALID_ARG;
+    if (!h->has_terrain) return MPPI_ERR_NO_TERRAIN;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    if (!h->loop_state) {
+        CK(cudaMalloc((void**)&h->loop_state, sizeof(MppiState)));
+        CK(cudaMalloc((void**)&h->loop_ctl, 2 * sizeof(int32_t)));
+    }
+    if (log_host && h->loop_log_cap < max_iters) {
+        if (h->loop_log) CK(cudaFree(h->loop_log));
+        h->loop_log = nullptr; h->loop_log_cap = 0;
+        CK(cudaMalloc((void**)&h->loop_log, (size_t)max_iters * 8 * sizeof(float)));
+        h->loop_log_cap = max_iters;
+    }
+    CK(cudaMemcpyAsync(h->loop_state, state_inout, sizeof(MppiState), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->loop_ctl, 0, 2 * sizeof(int32_t), s));
+    LoopCtl lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.state = h->loop_state; lc.ctl = h->loop_ctl; lc.log = log_host ? h->loop_log : nullptr;
+    lc.goal_tol = goal_tol; lc.sigma_base = sigma_base; lc.sigma_gain = sigma_gain;
+    // Launches are enqueued back to back; a launch that finds the goal flag set returns at once.  The host looks at
+    // the flag every `kCheck` iterations only, so the device never waits for it.
+    const int kCheck = 64;
+    const size_t noise_stride = (size_t)2 * h->p.K * h->p.T;
+    int32_t ctl[2] = { 0, 0 };
+    for (int it = 0; it < max_iters; ++it) {
+        lc.iter = it;
+        int rc = do_step(h, nullptr, nullptr, 1, proj, noise_dev ? noise_dev + (size_t)it * noise_stride : nullptr,
+                         seed, offset0 + (uint64_t)it, 0u, nullptr, s, false, false, &lc);
+        if (rc != MPPI_OK) return rc;
+        if ((it + 1) % kCheck == 0 && it + 1 < max_iters) {
+            CK(cudaMemcpyAsync(ctl, h->loop_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (ctl[1]) break;
+        }
+    }
+    CK(cudaMemcpyAsync(ctl, h->loop_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(state_inout, h->loop_state, sizeof(MppiState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (log_host && ctl[0] > 0)
+        CK(cudaMemcpy(log_host, h->loop_log, (size_t)ctl[0] * 8 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (iters_done) *iters_done = ctl[0];
+    if (goal_reached) *goal_reached = ctl[1];
+    return MPPI_OK;
 }
 
 extern "C" int mppi_sim_rollout(MppiHandle* h, const MppiState* state, void* stream)

@@ -362,6 +362,47 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
     if (tr != nullptr && tid == 0) tr[15] = globaltimer_ns();
 }
 
+// ------------------------------------------------------------------ closed loop: the plant step (one thread)
+// Launch 9 of the reference restricted to the step run() consumes (MPPI_isaac.py:696-720, :769-772), followed by the
+// host logic of run() (:774-784).  All float32 in the reference's order (run() keeps float32 NumPy scalars / arrays).
+__device__ void loop_advance(const FusedArgs& A, const MppiState& st, const float* stats)
+{
+    const MppiParams& p = A.p;
+    const float v0 = stats[6], w0 = stats[7];
+    const Terr ter = make_terr(A.terrain);
+    int oob = 0, i, j;
+    float dev = 0.0f;
+    float x = st.x, y = st.y;
+    Quad q = corners(ter, x, y, i, j, oob);
+    float3 n = normal_on_grid(q, ter.res);
+    float3 prev = tangent(n, make_float3(st.hx, st.hy, st.hz));
+    update_position(x, y, prev, v0, p.dt, dev);
+    q = corners(ter, x, y, i, j, oob);
+    const float z = bilinear(x, y, q, ter.rres);
+    n = normal_on_grid(q, ter.res);
+    prev = tangent(n, prev);
+    const float3 cur = update_orientation(prev, w0, n, p.dt, dev);
+
+    MppiState ns = st;
+    ns.x = x; ns.y = y;
+    // reset("controller"): heading / np.linalg.norm(heading) on the float32 array run() stored (MPPI_isaac.py:493)
+    const Recip rn = make_recip(fsqrt(cur.x * cur.x + cur.y * cur.y + cur.z * cur.z));
+    ns.hx = fdiv(cur.x, rn); ns.hy = fdiv(cur.y, rn); ns.hz = fdiv(cur.z, rn);
+    const float w2 = w0 * w0;
+    ns.sigma1 = fmaxf(A.loop.sigma_base, A.loop.sigma_base - A.loop.sigma_gain * w2);
+    ns.sigma2 = fmaxf(A.loop.sigma_base, A.loop.sigma_base + A.loop.sigma_gain * w2);
+    ns.wheel_l = v0 - w0 * p.r_wheels / 2.0f;
+    ns.wheel_r = v0 + w0 * p.r_wheels / 2.0f;
+    *A.loop.state = ns;
+    if (A.loop.log != nullptr) {
+        float* row = A.loop.log + (size_t)A.loop.iter * 8;
+        row[0] = x; row[1] = y; row[2] = z; row[3] = cur.x; row[4] = cur.y; row[5] = cur.z; row[6] = v0; row[7] = w0;
+    }
+    A.loop.ctl[0] = A.loop.iter + 1;
+    const bool far = fabsf(x - st.goal_x) > A.loop.goal_tol || fabsf(y - st.goal_y) > A.loop.goal_tol;
+    if (!far) A.loop.ctl[1] = 1;
+}
+
 // ------------------------------------------------------------------ phases 2 + 3, shared by both fused kernels
 // Every thread of the block calls this.  `valid` threads own one sample each (local index `k_in_block`, cost
 // `cost`); `spb` = samples per block.  INJECT: u is re-read from the injected noise instead of regenerated.
@@ -494,6 +535,8 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
                          A.rank_partial ? A.rank_partial + (size_t)rover * stride : nullptr, oob_count, nan_count,
                          (A.trace != nullptr && rover == 0) ? A.trace + (size_t)blockIdx.x * kTraceSlots : nullptr,
                          (rover == 0) ? A.host_cmd : nullptr, A.host_seq, (rover == 0) ? &A.peers : nullptr);
+    if (tid == 0 && A.loop.state != nullptr && A.rank_partial == nullptr)
+        loop_advance(A, st, A.stats + (size_t)rover * kStatsStride);
     if (tid == 0) {                                       // re-arm for the next launch
         trace_stamp(A, 6);
         A.counters[rover * kCounterStride + 0] = 0u;
@@ -556,7 +599,8 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
         }
     }
 
-    const MppiState st = (A.states != nullptr) ? A.states[rover] : A.state;
+    if (A.loop.state != nullptr && *reinterpret_cast<volatile const int32_t*>(A.loop.ctl + 1) != 0) return;   // goal reached
+    const MppiState st = (A.loop.state != nullptr) ? *A.loop.state : ((A.states != nullptr) ? A.states[rover] : A.state);
     const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
     const Terr ter = make_terr(tr);
     const SampleConsts sc = make_consts(p, st);
@@ -678,7 +722,8 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         }
     }
 
-    const MppiState st = (A.states != nullptr) ? A.states[rover] : A.state;
+    if (A.loop.state != nullptr && *reinterpret_cast<volatile const int32_t*>(A.loop.ctl + 1) != 0) return;   // goal reached
+    const MppiState st = (A.loop.state != nullptr) ? *A.loop.state : ((A.states != nullptr) ? A.states[rover] : A.state);
     const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
     const Terr ter = make_terr(tr);
     const SampleConsts sc = make_consts(p, st);

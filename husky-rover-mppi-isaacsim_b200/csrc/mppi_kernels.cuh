@@ -30,6 +30,20 @@ struct PeerComm {
     uint32_t seq;                     // step sequence number (parity = seq & 1 selects the buffer half)
 };
 
+// Device-resident closed loop (mppi_run_closed_loop): the plant of MPPI_Controller.run (MPPI_isaac.py:755-805) is the
+// controller's own model, so the whole loop can stay on the device.  The fused kernel reads its MppiState from
+// `state` and, once (v*, w*) are known, thread 0 of the last block advances the robot by the first step of the
+// optimal-trajectory rollout (launch 9, MPPI_isaac.py:696-720) and applies run()'s host logic (:769-784) to produce
+// the next iteration's state -- one launch per control iteration, no host round trip.
+struct LoopCtl {
+    MppiState* state;                 // device, in/out; nullptr: loop mode off
+    float* log;                       // device [max_iters][8] {x, y, z, hx, hy, hz, v*, w*} after each iteration, or nullptr
+    int32_t* ctl;                     // device {iterations done, goal reached}
+    float goal_tol;                   // stop when |x - goal_x| <= tol and |y - goal_y| <= tol   (0.5, MPPI_isaac.py:763)
+    float sigma_base, sigma_gain;     // sigma1/2 = max(base, base -/+ gain * w^2)                (0.4, 1: MPPI_isaac.py:777-778)
+    int32_t iter;                     // index of this iteration (row of `log`)
+};
+
 struct FusedArgs {
     MppiParams p;
     MppiState state;                  // used when states == nullptr
@@ -55,6 +69,7 @@ struct FusedArgs {
     float* host_cmd;                  // optional mapped pinned host memory [4]: {v*, w*, sequence, 0} (mppi_step_host)
     uint32_t host_seq;                // sequence number stored with the command
     PeerComm peers;                   // sample-sharded multi-GPU exchange (world == 0: off)
+    LoopCtl loop;                     // device-resident closed loop (state == nullptr: off)
 };
 
 struct CombineArgs {

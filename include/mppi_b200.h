@@ -200,6 +200,21 @@ int mppi_step_sharded_host(MppiHandle *h, const MppiState *state, int32_t proj, 
  * filling sim_traj / sim_heading. Lazy: only run() consumes element [0] (MPPI_isaac.py:769-772). */
 int mppi_sim_rollout(MppiHandle *h, const MppiState *state, void *stream);
 
+/* Replaces the offline closed loop MPPI_Controller.run (MPPI_isaac.py:755-805), whose plant is the controller's own
+ * model, with a device-resident loop: one fused launch per control iteration, the robot state lives in device memory.
+ * After (v*, w*) are known, the launch's last block advances the robot by the first step of the optimal-trajectory
+ * rollout (launch 9, MPPI_isaac.py:696-720, :769-772) and applies run()'s host logic -- sigma1/2 = max(b, b -/+ g w^2)
+ * (:777-778, b = sigma_base = 0.4, g = sigma_gain = 1), wheel speeds v -/+ w r/2 (:783-784), goal test
+ * abs(x - gx) <= goal_tol and abs(y - gy) <= goal_tol (:763, 0.5) -- so no host round trip happens until the loop ends.
+ *  state_inout: host; in: the initial state, out: the state after the last executed iteration.
+ *  noise_dev:   NULL (Philox, offset = offset0 + iteration) or device [max_iters][2][K][T] injected noise.
+ *  log_host:    optional host [max_iters][8] rows {x, y, z, hx, hy, hz, v*, w*} per executed iteration (what run()
+ *               appends to robot.x / y / z, heading_vector, lin_vel, ang_vel).
+ * Synchronous: returns when the loop has ended (goal reached or max_iters). */
+int mppi_run_closed_loop(MppiHandle *h, MppiState *state_inout, int32_t proj, const float *noise_dev,
+                         uint64_t seed, uint64_t offset0, int32_t max_iters, float goal_tol, float sigma_base,
+                         float sigma_gain, float *log_host, int32_t *iters_done, int32_t *goal_reached, void *stream);
+
 /* Validation / visualiser path: re-runs sampling + rollout + critics for rover 0 and writes the requested
  * K x T intermediates (what the unfused reference keeps in `trajectories`, `left_wheel_pos`, ...). Uses the
  * nominal sequence as it was BEFORE the last step when `use_previous_nominal` != 0. */

@@ -195,3 +195,64 @@ def test_facade_run_loop_matches_the_reference_run_loop(gold, tmp_path):
     got = np.array([robot.x[-1], robot.y[-1], robot.z[-1], *np.asarray(robot.heading_vector)], np.float64)
     assert np.max(np.abs(got - final)) < 1e-5
     ctrl.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_run_loop_matches_the_reference_run_loop(gold, tmp_path):
+    """f2: the closed loop of run() resident on the device (one fused launch per iteration, plant step and host
+    feedback logic inside the kernel) against the reference's run(): same poses after every iteration, same sigma /
+    wheel-speed feedback, same final pose -- and bit-identical to our own host loop."""
+    import torch
+    import yaml
+    from mppi_b200 import MPPI_Controller, Robot, Surface
+    name = "A3d"
+    sc = scenario(gold, name)
+    cfg = dict(frame_work=dict(robot_radius=sc["radius"]),
+               controller=dict(number_of_iterations=sc["T"], dt=0.045, number_of_trajectories=sc["K"]),
+               velocities=dict(initial_linear_velocity=0.0, min_linear_velocity=0.0, max_linear_velocity=2.0,
+                               initial_angular_velocity=0.0, min_angular_velocity=-1.0, max_angular_velocity=1.0),
+               inputs=dict(std_dev_u1=0.25, std_dev_u2=0.25, min_u1=-1, max_u1=1, min_u2=-1, max_u2=1),
+               cost_evaluation=dict(temperature=sc["lam"]))
+    path = tmp_path / "config.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    g0 = lambda k: gold[f"{name}/step0/in/{k}"]                                  # noqa: E731
+    eps = torch.from_numpy(np.stack([np.stack([gold[f"{name}/step{s}/out/eps1"], gold[f"{name}/step{s}/out/eps2"]])
+                                     for s in range(sc["n"])])).cuda()
+
+    def make():
+        surface = Surface("none", "", "none", "", sc["gs"], sc["hw"], (0.0, 0.0), [], 0.3)
+        surface.Z, surface.costmap = sc["Z"], sc["cm"]
+        robot = Robot(float(g0("x")), float(g0("y")), g0("heading"), str(path))
+        robot.left_wheel_speed, robot.right_wheel_speed = float(g0("wheel_l")), float(g0("wheel_r"))
+        return robot, MPPI_Controller(surface, robot, str(path), sc["gx"], sc["gy"], 2.2)
+
+    robot_d, ctrl_d = make()
+    ctrl_d.inject_noise(eps)
+    ctrl_d.loop = 3500 - sc["n"]
+    ctrl_d.run("3d", device_loop=True)
+    # the reference's recorded inputs of iterations 1.. are the poses / feedback produced by iterations 0..
+    for s in range(1, sc["n"]):
+        nxt = lambda k: gold[f"{name}/step{s}/in/{k}"]                           # noqa: E731
+        assert abs(robot_d.x[s] - float(nxt("x"))) < 1e-5 and abs(robot_d.y[s] - float(nxt("y"))) < 1e-5
+    final = gold[name + "/final_pose"]
+    got = np.array([robot_d.x[-1], robot_d.y[-1], robot_d.z[-1], *np.asarray(robot_d.heading_vector)], np.float64)
+    assert np.max(np.abs(got - final)) < 1e-5
+    assert ctrl_d.loop == 3500
+
+    robot_h, ctrl_h = make()
+    real_step = ctrl_h.MPPI_step
+
+    def step_with_recorded_noise(proj="3d"):
+        ctrl_h.inject_noise(eps[ctrl_h.loop - (3500 - sc["n"])])
+        real_step(proj=proj)
+
+    ctrl_h.MPPI_step = step_with_recorded_noise
+    ctrl_h.loop = 3500 - sc["n"]
+    ctrl_h.run("3d")
+    assert np.array_equal(np.asarray(robot_d.x, np.float32), np.asarray(robot_h.x, np.float32))
+    assert np.array_equal(np.asarray(robot_d.y, np.float32), np.asarray(robot_h.y, np.float32))
+    assert np.array_equal(np.asarray(robot_d.heading_vector, np.float32), np.asarray(robot_h.heading_vector, np.float32))
+    assert np.float32(ctrl_d.std_dev_u2) == np.float32(ctrl_h.std_dev_u2)
+    assert np.float32(robot_d.left_wheel_speed) == np.float32(robot_h.left_wheel_speed)
+    ctrl_d.close()
+    ctrl_h.close()

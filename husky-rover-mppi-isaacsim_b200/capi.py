@@ -97,6 +97,9 @@ SYMBOLS = {
     "mppi_sim_rollout": (C.c_int, [_H, C.POINTER(MppiState), C.c_void_p]),
     "mppi_debug_dump": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32,
                                   C.POINTER(MppiDebugDump), C.c_void_p]),
+    "mppi_build_costmap": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
+                                     C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "mppi_get_outputs": (C.c_int, [_H, C.POINTER(MppiOutputs)]),
     "mppi_enable_timing": (C.c_int, [_H, C.c_int32]),
     "mppi_last_step_us": (C.c_int, [_H, C.POINTER(C.c_float)]),

@@ -210,6 +210,25 @@ class MPPI_Controller:
         self._Z = to_device_f32(arr, self.device)
         self._terrain_dirty = True
 
+    def rebuild_costmap(self, obstacles, origin, power: float = 20.0):
+        """Block-change path of the Isaac driver (visual_terrain_stack_full_terrain.py:561-563:
+        `surface.costmap = surface.create_obstacles_costmap(...)`; `costmap_wp.assign(surface.costmap.flatten())`) done
+        on the device: rocks -> distance transform -> (1 - d)^p written straight into `costmap_wp`.  `surface.costmap`
+        is refreshed lazily from the device copy only if somebody reads it (`surface_costmap()`)."""
+        from .costmap import build_obstacle_costmap
+        s = self.surface
+        s.obstacles = obstacles
+        build_obstacle_costmap(obstacles, origin, int(s.costmap_size), float(s.half_width), float(s.r_robot),
+                               out=self.costmap_wp.tensor.view(int(s.costmap_size), int(s.costmap_size)),
+                               device=self.device.index, power=power)
+        self._terrain_dirty = True
+
+    def surface_costmap(self) -> np.ndarray:
+        """Host copy of the device costmap (refreshes `surface.costmap`)."""
+        n = int(self.surface.costmap_size)
+        self.surface.costmap = self.costmap_wp.tensor.view(n, n).cpu().numpy()
+        return self.surface.costmap
+
     def _push_terrain(self):
         s = self.surface
         gs, cms = int(s.grid_size), int(s.costmap_size)

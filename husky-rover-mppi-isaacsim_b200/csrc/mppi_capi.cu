@@ -529,6 +529,59 @@ extern "C" int mppi_set_trace(MppiHandle* h, uint64_t* trace_dev, int32_t* nbloc
     return MPPI_OK;
 }
 
+// ---------------------------------------------------------------- obstacle costmap builder
+namespace mppi { namespace costmap {
+cudaError_t build(const double* obstacles_dev, int n_obs, double x0, double y0, int cms, double hw, double r_robot,
+                  double radius_scale, double inflate, double power, uint8_t* mask, float* tmp, float* dist, float* minmax,
+                  float* costmap, cudaStream_t s);
+} }
+
+struct CostmapWorkspace {          // grown on demand, one per process (the builder is not re-entrant)
+    int device = -1;
+    size_t cells = 0, obs = 0;
+    uint8_t* mask = nullptr; float* tmp = nullptr; float* dist = nullptr; float* minmax = nullptr; double* obstacles = nullptr;
+};
+static CostmapWorkspace g_cm;
+
+extern "C" int mppi_build_costmap(int32_t device, const double* obstacles_host, int32_t n_obs, double origin_x,
+                                  double origin_y, int32_t costmap_size, double half_width, double r_robot,
+                                  double radius_scale, double inflate, double power, float* costmap_dev,
+                                  float* distance_dev, unsigned char* mask_dev, void* stream)
+{
+    if (n_obs < 0 || (n_obs > 0 && !obstacles_host) || costmap_size < 2 || costmap_size > 1024 || !(half_width > 0.0) ||
+        !costmap_dev)
+        return (costmap_size > 1024) ? MPPI_ERR_UNSUPPORTED : MPPI_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(device));
+    const size_t cells = (size_t)costmap_size * costmap_size;
+    if (g_cm.device != device || g_cm.cells < cells) {
+        if (g_cm.mask) { cudaFree(g_cm.mask); cudaFree(g_cm.tmp); cudaFree(g_cm.dist); cudaFree(g_cm.minmax); }
+        g_cm.mask = nullptr; g_cm.cells = 0;
+        CK(cudaMalloc((void**)&g_cm.mask, cells));
+        CK(cudaMalloc((void**)&g_cm.tmp, cells * sizeof(float)));
+        CK(cudaMalloc((void**)&g_cm.dist, cells * sizeof(float)));
+        CK(cudaMalloc((void**)&g_cm.minmax, 2 * sizeof(float)));
+        g_cm.cells = cells;
+        if (g_cm.device != device) { if (g_cm.obstacles) cudaFree(g_cm.obstacles); g_cm.obstacles = nullptr; g_cm.obs = 0; }
+        g_cm.device = device;
+    }
+    if ((size_t)n_obs > g_cm.obs) {
+        if (g_cm.obstacles) cudaFree(g_cm.obstacles);
+        g_cm.obstacles = nullptr; g_cm.obs = 0;
+        CK(cudaMalloc((void**)&g_cm.obstacles, (size_t)n_obs * 3 * sizeof(double)));
+        g_cm.obs = (size_t)n_obs;
+    }
+    if (n_obs > 0)
+        CK(cudaMemcpyAsync(g_cm.obstacles, obstacles_host, (size_t)n_obs * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    cudaError_t e = mppi::costmap::build(g_cm.obstacles, n_obs, origin_x, origin_y, costmap_size, half_width, r_robot,
+                                         radius_scale, inflate, power, g_cm.mask, g_cm.tmp, g_cm.dist, g_cm.minmax,
+                                         costmap_dev, s);
+    if (e != cudaSuccess) return cuda_fail(e, "mppi_build_costmap");
+    if (distance_dev) CK(cudaMemcpyAsync(distance_dev, g_cm.dist, cells * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (mask_dev) CK(cudaMemcpyAsync(mask_dev, g_cm.mask, cells, cudaMemcpyDeviceToDevice, s));
+    return MPPI_OK;
+}
+
 extern "C" int mppi_test_detmath(int32_t fn, const float* x, float* y0, float* y1, int32_t n, void* stream)
 {
     if (!x || !y0 || n < 1 || fn < 0 || fn > 3) return MPPI_ERR_INVALID_ARG;

@@ -222,6 +222,21 @@ int mppi_debug_dump(MppiHandle *h, const MppiState *state, int32_t proj, const f
                     uint64_t seed, uint64_t offset, int32_t use_previous_nominal,
                     const MppiDebugDump *dump, void *stream);
 
+/* Replaces Surface.create_obstacles_costmap (MPPI_isaac.py:361-378; called at start-up and at every terrain-block
+ * change, visual_terrain_stack_full_terrain.py:449,561-563): rocks -> inflated discs (float64 test on the
+ * numpy.linspace grid, identical mask) -> two-pass 5x5 chamfer distance (what cv2.distanceTransform(DIST_L2, 5)
+ * computes: weights 1, 1.4, 2.1969, float32 path sums) -> min-max normalisation (cv2.normalize NORM_MINMAX) ->
+ * (1 - d)^power, written straight into a device costmap (no host round trip, no H2D).
+ *  obstacles_host: [n_obs][3] doubles (x_global, y_global, r_obs); a rock covers the cells within
+ *                  r_obs * radius_scale + r_robot + inflate of (y_global - origin_y, x_global - origin_x)  (:365-372;
+ *                  radius_scale 0.5, inflate 0.1, power 20 in MPPI_isaac.py; 1, 0.2, 10 in create_costmap.py:14-28).
+ *  costmap_dev:    device [costmap_size^2] float out (e.g. the buffer passed to mppi_set_terrain).
+ *  distance_dev / mask_dev: optional device outputs of the intermediate distance map (float) and mask (uint8).
+ * costmap_size <= 1024 (MPPI_ERR_UNSUPPORTED above).  Asynchronous on `stream`; not re-entrant (one workspace). */
+int mppi_build_costmap(int32_t device, const double *obstacles_host, int32_t n_obs, double origin_x, double origin_y,
+                       int32_t costmap_size, double half_width, double r_robot, double radius_scale, double inflate,
+                       double power, float *costmap_dev, float *distance_dev, unsigned char *mask_dev, void *stream);
+
 int mppi_get_outputs(MppiHandle *h, MppiOutputs *out);
 
 /* Last measured device time of mppi_step* in microseconds (CUDA events on the step's stream); optional

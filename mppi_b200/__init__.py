@@ -9,6 +9,7 @@ __path__.insert(0, _PKG_DIR)
 from . import capi                                            # noqa: E402
 from .controller import MPPI_Controller, Robot, Surface       # noqa: E402
 from .devarray import DeviceArray                             # noqa: E402
+from .costmap import build_obstacle_costmap                   # noqa: E402
 
 DEFAULT_CONFIG = _os.path.join(_PKG_DIR, "config", "default.yaml")
-__all__ = ["capi", "MPPI_Controller", "Robot", "Surface", "DeviceArray", "DEFAULT_CONFIG"]
+__all__ = ["capi", "MPPI_Controller", "Robot", "Surface", "DeviceArray", "DEFAULT_CONFIG", "build_obstacle_costmap"]

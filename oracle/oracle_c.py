@@ -66,7 +66,7 @@ class OrOut(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
-    srcs = [os.path.join(_HERE, f) for f in ("mppi_oracle.c", "mppi_oracle.h", "det_math.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("mppi_oracle.c", "mppi_oracle.h", "det_math.h", "costmap_oracle.c", "Makefile")]
     if (not force and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
@@ -241,3 +241,41 @@ def combine_partials(parts: np.ndarray, T: int, lam: float, math: int = MATH_DET
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+# ------------------------------------------------------------------ obstacle costmap (MPPI_isaac.py:361-378)
+def chamfer5x5(mask: np.ndarray) -> np.ndarray:
+    """cv2.distanceTransform(mask, DIST_L2, 5) restated (two-pass 5x5 chamfer, 16.16 fixed point)."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.zeros(mask.shape, np.float32)
+    rc = lib().oracle_chamfer5x5(mask.ctypes.data_as(C.c_void_p), mask.shape[0], mask.shape[1],
+                                 out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("oracle_chamfer5x5 failed")
+    return out
+
+
+def rasterize_obstacles(obstacles, origin, cms: int, half_width: float, r_robot: float, radius_scale: float = 0.5,
+                        inflate: float = 0.1) -> np.ndarray:
+    obs = np.ascontiguousarray(np.asarray(obstacles, np.float64).reshape(-1, 3))
+    mask = np.zeros((cms, cms), np.uint8)
+    f = lib().oracle_rasterize_obstacles
+    f.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
+                  C.c_double, C.c_void_p]
+    rc = f(obs.ctypes.data_as(C.c_void_p), obs.shape[0], float(origin[0]), float(origin[1]), cms, float(half_width),
+           float(r_robot), float(radius_scale), float(inflate), mask.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("oracle_rasterize_obstacles failed")
+    return mask
+
+
+def obstacle_costmap(obstacles, origin, cms: int, half_width: float, r_robot: float, power: float = 20.0,
+                     radius_scale: float = 0.5, inflate: float = 0.1):
+    """Surface.create_obstacles_costmap restated: (mask, distance, costmap float32)."""
+    mask = rasterize_obstacles(obstacles, origin, cms, half_width, r_robot, radius_scale, inflate)
+    d = chamfer5x5(mask)
+    smin, smax = float(d.min()), float(d.max())
+    scale = (1.0 / (smax - smin)) if (smax - smin) > np.finfo(np.float64).eps else 0.0      # cv2.normalize, NORM_MINMAX
+    shift = 0.0 - smin * scale
+    dn = (d * np.float32(scale) + np.float32(shift)).astype(np.float32)
+    return mask, d, ((np.float32(1) - dn) ** power).astype(np.float32)

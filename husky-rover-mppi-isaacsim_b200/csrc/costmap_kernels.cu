@@ -13,7 +13,7 @@
 //                                   the wavefronts with one thread per row: the left neighbour stays in a register,
 //                                   the two rows above are read from 16-deep shared-memory rings written by the
 //                                   neighbouring threads.  Same candidates, same float operations as the sequential
-//                                   scan -> bit-identical to oracle/costmap_oracle.c.  2 x (cols + 3 rows) barriers.
+//                                   scan -> bit-identical to the CPU restatement used by the tests.  2 x (cols + 3 rows) barriers.
 //   k3  costmap_finish_kernel      min / max come out of k2; d * scale + shift (cv2.normalize), (1 - d)^p.
 //
 // Compiled with the STRICT flags (no FMA contraction: NumPy does not contract either).

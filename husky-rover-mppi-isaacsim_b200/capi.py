@@ -100,6 +100,8 @@ SYMBOLS = {
     "mppi_build_costmap": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "mppi_export_trajectories": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mppi_get_outputs": (C.c_int, [_H, C.POINTER(MppiOutputs)]),
     "mppi_enable_timing": (C.c_int, [_H, C.c_int32]),
     "mppi_last_step_us": (C.c_int, [_H, C.POINTER(C.c_float)]),

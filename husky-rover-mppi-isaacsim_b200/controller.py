@@ -332,6 +332,41 @@ class MPPI_Controller:
                    "mppi_debug_dump")
         return out
 
+    def visualiser_points(self, block_x_current: float, block_y_current: float, half_block: float,
+                          sample_stride: int = 50, step_stride: int = 10):
+        """What the driver hands to VisualizeMPPI (visual_terrain_stack_full_terrain.py:252-261, 520-528):
+        every `sample_stride`-th sampled trajectory of the last step at every `step_stride`-th step, moved into the
+        world frame (x_w = -y + block_x + half_block, y_w = x + block_y + half_block), and the matching costs
+        normalised as `(c - min(c)) / max(c)` and repeated per point.  Returns NumPy (points [n, 3], costs [n])."""
+        K, T = self.number_of_trajectories, self.number_of_iterations
+        ne, nt = -(-K // sample_stride), -(-T // step_stride)
+        pts = torch.empty((ne, nt, 3), dtype=torch.float32, device=self.device)
+        st = self._last_state if self._last_state is not None else self._state()
+        noise = self._injected_noise.data_ptr() if self._injected_noise is not None else None
+        capi.check(self._lib.mppi_export_trajectories(self._handle, C.byref(st), self._last_proj, noise, self.seed,
+                                                      self._last_offset, 1, sample_stride, step_stride,
+                                                      pts.data_ptr(), self._stream), "mppi_export_trajectories")
+        p = pts.reshape(-1, 3)
+        # float32 additions in the driver's order: (-y + block_x) + half_block
+        world = torch.stack([(-p[:, 1] + block_x_current) + half_block, (p[:, 0] + block_y_current) + half_block,
+                             p[:, 2]], dim=1)
+        costs = self.costs_wp.tensor[::sample_stride]
+        costs = (costs - costs.min()) / costs.max()
+        return world.cpu().numpy(), costs.repeat_interleave(nt).cpu().numpy()
+
+    def on_block_change(self, shift_x: float, shift_y: float, dem, rocks_data, origin):
+        """The driver's terrain-block change (visual_terrain_stack_full_terrain.py:546-576) in one call: rebuild the
+        obstacle costmap for the new block on the device, swap the DEM pointer (zero-copy when `dem` is a device
+        array), and shift the robot history and the goal into the new block frame."""
+        self.rebuild_costmap(rocks_data, origin)
+        self.Z_wp = dem
+        for j in range(len(self.robot.x)):
+            self.robot.x[j] -= shift_y
+            self.robot.y[j] += shift_x
+        self.goal_x -= shift_y
+        self.goal_y += shift_x
+        self.goal = (self.goal_x, self.goal_y)
+
     @property
     def trajectories(self):
         """K*T x 3 sampled trajectories of the last step (MPPI_isaac.py:467), materialised on access."""

@@ -493,6 +493,26 @@ extern "C" int mppi_debug_dump(MppiHandle* h, const MppiState* state, int32_t pr
     return MPPI_OK;
 }
 
+extern "C" int mppi_export_trajectories(MppiHandle* h, const MppiState* state, int32_t proj, const float* noise_dev,
+                                        uint64_t seed, uint64_t offset, int32_t use_previous_nominal, int32_t k_stride,
+                                        int32_t t_stride, float* points_dev, void* stream)
+{
+    if (!h || !state || !points_dev || k_stride < 1 || t_stride < 1 || (proj != MPPI_PROJ_2D && proj != MPPI_PROJ_3D))
+        return MPPI_ERR_INVALID_ARG;
+    if (!h->has_terrain) return MPPI_ERR_NO_TERRAIN;
+    CK(cudaSetDevice(h->device));
+    ExportArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = h->p; a.state = *state; a.terrain = h->terrain; a.noise = noise_dev;
+    a.nominal1 = use_previous_nominal ? h->prev1 : h->nominal1;
+    a.nominal2 = use_previous_nominal ? h->prev2 : h->nominal2;
+    a.seed = seed; a.offset = offset; a.k_stride = k_stride; a.t_stride = t_stride; a.points = points_dev;
+    cudaError_t e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_export(a, proj, (cudaStream_t)stream)
+                                                  : strict::launch_export(a, proj, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_export");
+    return MPPI_OK;
+}
+
 extern "C" int mppi_get_outputs(MppiHandle* h, MppiOutputs* out)
 {
     if (!h || !out) return MPPI_ERR_INVALID_ARG;

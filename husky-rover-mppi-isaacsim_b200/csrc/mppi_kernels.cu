@@ -968,6 +968,51 @@ __global__ void __launch_bounds__(128) mppi_dump_kernel(const __grid_constant__ 
     if (A.d.critics) { for (int i = 0; i < 4; ++i) A.d.critics[4 * k + i] = cr[i]; }
 }
 
+// Strided export for the visualiser: the driver shows every 50th sampled trajectory at every 10th step
+// (visual_terrain_stack_full_terrain.py:252-261, 520-528), i.e. 2 % of the samples and 0.2 % of the K x T points.
+// One thread per exported sample re-rolls it (same device functions, same bits as the step) and stores only the
+// requested points.
+template <int PROJ, bool INJECT>
+__global__ void __launch_bounds__(128) mppi_export_kernel(const __grid_constant__ ExportArgs A)
+{
+    const MppiParams& p = A.p;
+    const int T = p.T, K = p.K;
+    const int ke = blockIdx.x * blockDim.x + threadIdx.x;          // exported sample index
+    const int k = ke * A.k_stride;
+    if (k >= K) return;
+    const int nt = (T + A.t_stride - 1) / A.t_stride;
+    const Terr ter = make_terr(A.terrain);
+    const SampleConsts sc = make_consts(p, A.state);
+    const NoiseKey nk = make_noise_key(A.seed, A.offset, 0u);
+    const UBounds ub = make_ubounds(p);
+    DumpPtrs none = {}, pts = {};
+    pts.traj = A.points;
+    SampleAcc a;
+    sample_init<PROJ>(A.state, ter, a);
+    const float* eps1 = INJECT ? A.noise + (size_t)k * T : nullptr;
+    const float* eps2 = INJECT ? eps1 + (size_t)K * T : nullptr;
+    for (int t = 0; t < T; t += 2) {
+        float e1a, e1b, e2a, e2b;
+        if (INJECT) {
+            e1a = eps1[t]; e2a = eps2[t];
+            e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
+            e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
+        } else {
+            noise_pair(nk, (uint32_t)k, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int tt = t + h;
+            if (tt >= T) break;
+            const float u1 = sample_u(A.nominal1, tt, T, A.state.sigma1, h ? e1b : e1a, ub.lo1, ub.hi1);
+            const float u2 = sample_u(A.nominal2, tt, T, A.state.sigma2, h ? e2b : e2a, ub.lo2, ub.hi2);
+            const bool keep = (tt % A.t_stride) == 0;
+            sample_step<PROJ, true>(p, A.state, ter, sc, a, tt, u1, u2, keep ? pts : none,
+                                    (size_t)ke * nt + (size_t)(tt / A.t_stride));
+        }
+    }
+}
+
 // weights with the global minimum, as the reference intends (critics_warp.py:338-347, run_mppi.py:222-226)
 __global__ void __launch_bounds__(1024) mppi_weights_kernel(const float* costs, int K, float lambda, float* weights)
 {
@@ -1135,6 +1180,20 @@ cudaError_t launch_dump(const DumpArgs& a, int proj, cudaStream_t s)
     } else {
         if (a.noise) mppi_dump_kernel<MPPI_PROJ_2D, true><<<grid, block, 0, s>>>(a);
         else mppi_dump_kernel<MPPI_PROJ_2D, false><<<grid, block, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export(const ExportArgs& a, int proj, cudaStream_t s)
+{
+    const int ne = (a.p.K + a.k_stride - 1) / a.k_stride;
+    const int block = 128, grid = (ne + block - 1) / block;
+    if (proj == MPPI_PROJ_3D) {
+        if (a.noise) mppi_export_kernel<MPPI_PROJ_3D, true><<<grid, block, 0, s>>>(a);
+        else mppi_export_kernel<MPPI_PROJ_3D, false><<<grid, block, 0, s>>>(a);
+    } else {
+        if (a.noise) mppi_export_kernel<MPPI_PROJ_2D, true><<<grid, block, 0, s>>>(a);
+        else mppi_export_kernel<MPPI_PROJ_2D, false><<<grid, block, 0, s>>>(a);
     }
     return cudaGetLastError();
 }

@@ -93,6 +93,17 @@ struct DumpArgs {
     uint32_t k_begin;
 };
 
+struct ExportArgs {                  // strided trajectory export for the visualiser (driver transform_trajs :252-261)
+    MppiParams p;
+    MppiState state;
+    MppiTerrain terrain;
+    const float* noise;
+    const float* nominal1; const float* nominal2;
+    uint64_t seed, offset;
+    int32_t k_stride, t_stride;       // every k_stride-th sample, every t_stride-th step
+    float* points;                    // device [ceil(K / k_stride)][ceil(T / t_stride)][3]
+};
+
 struct SimArgs {
     MppiParams p;
     MppiState state;
@@ -107,6 +118,7 @@ struct SimArgs {
     cudaError_t launch_fused_pipe(const FusedArgs& a, int proj, int n_rovers, cudaStream_t s);                 \
     cudaError_t launch_combine(const CombineArgs& a, cudaStream_t s);                                          \
     cudaError_t launch_dump(const DumpArgs& a, int proj, cudaStream_t s);                                      \
+    cudaError_t launch_export(const ExportArgs& a, int proj, cudaStream_t s);                                  \
     cudaError_t launch_weights(const float* costs, int K, float lambda, float* weights, cudaStream_t s);      \
     cudaError_t launch_sim(const SimArgs& a, cudaStream_t s);                                                  \
     cudaError_t launch_detmath(int fn, const float* x, float* y0, float* y1, int n, cudaStream_t s);          \

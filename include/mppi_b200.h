@@ -237,6 +237,16 @@ int mppi_build_costmap(int32_t device, const double *obstacles_host, int32_t n_o
                        int32_t costmap_size, double half_width, double r_robot, double radius_scale, double inflate,
                        double power, float *costmap_dev, float *distance_dev, unsigned char *mask_dev, void *stream);
 
+/* Visualiser feed (visual_terrain_stack_full_terrain.py:252-261, 520-528; consumer
+ * src/terrain_management/large_scale_terrain/mppi_instancer.py:65-90): the driver shows every 50th sampled trajectory
+ * at every 10th step -- `trajectories.numpy().reshape(-1, T, 3)[::50]` then `[::10]` -- which in the reference costs a
+ * D2H copy of the whole K x T x 3 tensor.  This re-rolls only the requested samples of the LAST step and writes only
+ * the requested points: points_dev = device [ceil(K / k_stride)][ceil(T / t_stride)][3] (x, y, height).  Arguments as
+ * mppi_debug_dump. */
+int mppi_export_trajectories(MppiHandle *h, const MppiState *state, int32_t proj, const float *noise_dev, uint64_t seed,
+                             uint64_t offset, int32_t use_previous_nominal, int32_t k_stride, int32_t t_stride,
+                             float *points_dev, void *stream);
+
 int mppi_get_outputs(MppiHandle *h, MppiOutputs *out);
 
 /* Last measured device time of mppi_step* in microseconds (CUDA events on the step's stream); optional

@@ -257,3 +257,42 @@ def test_fused_peer_exchange_across_gpus(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTI_GPU_CHECK_OK" in r.stdout
+
+
+def test_visualiser_export_and_block_change(oracle):
+    """f4 + f3: the strided visualiser feed equals the reference's slicing of the full K x T tensor
+    (driver transform_trajs :252-261, :520-528), and the block-change call re-anchors history / goal and swaps maps."""
+    import torch
+    from mppi_b200 import DEFAULT_CONFIG, MPPI_Controller, Robot, Surface
+    dem, cm, hw = terrain("small")
+    surface = Surface("none", "", "none", "", dem.shape[0], hw, (0.0, 0.0), [], 0.3)
+    surface.Z, surface.costmap = dem, cm
+    surface.costmap_size, surface.costmap_resolution = cm.shape[0], 2 * hw / cm.shape[0]
+    robot = Robot(-3.0, -2.0, (1.0, 0.2, 0.0), DEFAULT_CONFIG)
+    ctrl = MPPI_Controller(surface, robot, DEFAULT_CONFIG, 6.0, 5.0, 2.2,
+                           overrides=dict(number_of_trajectories=600, number_of_iterations=100))
+    ctrl.warp_setup()
+    ctrl.MPPI_step("3d")
+    full = ctrl.trajectories.numpy()                                   # K*T x 3, as the reference keeps it
+    bx, by, half = 40.0, -25.0, 87.5
+    ref = full.reshape(-1, 100, 3)[::50].reshape(-1, 3)[::10]           # transform_trajs, verbatim slicing
+    want = ref.copy()
+    want[:, 0] = -ref[:, 1] + bx + half
+    want[:, 1] = ref[:, 0] + by + half
+    costs = ctrl.costs_wp.numpy()[::50]
+    want_c = ((costs - np.min(costs)) / np.max(costs)).repeat(10)
+    pts, cs = ctrl.visualiser_points(bx, by, half)
+    assert pts.shape == want.shape and np.array_equal(pts[:, 2], want[:, 2])
+    assert np.allclose(pts, want, rtol=0, atol=1e-5) and np.allclose(cs, want_c, rtol=1e-6)
+    # block change: history and goal move into the new block frame, the new maps are live
+    x_before, gx, gy = list(robot.x), ctrl.goal_x, ctrl.goal_y
+    new_dem = torch.from_numpy(np.ascontiguousarray(dem[::-1])).cuda()
+    ctrl.on_block_change(3.0, -2.0, new_dem, [(1.0, 1.0, 0.8), (-2.0, 3.0, 0.5)], (5.0, 6.0))
+    assert robot.x == [x + 2.0 for x in x_before] and ctrl.goal_x == gx + 2.0 and ctrl.goal_y == gy + 3.0
+    assert ctrl.Z_wp.tensor.data_ptr() == new_dem.data_ptr()             # zero-copy swap
+    want_cm = oracle.obstacle_costmap([(1.0, 1.0, 0.8), (-2.0, 3.0, 0.5)], (5.0, 6.0), int(surface.costmap_size), hw, 0.3)[2]
+    assert np.allclose(ctrl.surface_costmap(), want_cm, rtol=2e-5, atol=1e-7)
+    ctrl.MPPI_step("3d")
+    torch.cuda.synchronize()
+    assert ctrl.stats()["nan"] == 0
+    ctrl.close()

@@ -709,7 +709,12 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     extern __shared__ __align__(16) float smem_raw[];
     const MppiParams& p = A.p;
     const int T = p.T, K = p.K, tid = threadIdx.x;
-    const int lane = tid & 31, role = tid >> 5;
+    const int lane = tid & 31;
+    // Warp w issues on SM sub-partition w % 4.  When two CTAs share an SM (grids beyond one CTA per SM: the second
+    // wave of the block rasteriser lands on the same SMs), every second CTA swaps the chain and wheel warps so that the
+    // two dependent chains do not compete for the same scheduler.
+    int role = tid >> 5;
+    if (((blockIdx.x / 148) & 1) && (role == 2 || role == 3)) role ^= 1;
     const int rover = blockIdx.y;
     const Smem s = carve(smem_raw, T, kPipeThreads, A.nblocks);
     PipeSmem& ps = *reinterpret_cast<PipeSmem*>(smem_raw + pipe_smem_offset_floats(T, A.nblocks));

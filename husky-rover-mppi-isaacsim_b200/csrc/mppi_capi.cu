@@ -4,6 +4,8 @@
 #include "mppi_kernels.cuh"
 
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -226,6 +228,28 @@ extern "C" int mppi_get_nominal(MppiHandle* h, float* u1, float* u2, int32_t n_r
     return MPPI_OK;
 }
 
+// Geometry of the shared-memory DEM tile of the pipelined kernel (DemTile in mppi_kernels.cuh): the cells the body can
+// reach in T steps plus a margin, with 16-byte aligned rows for the TMA bulk copies.  Returns w = 0 (no tile) when the
+// tile would not fit beside the pipeline's rings, the rows cannot be aligned, or the window touches the map border.
+static DemTile plan_dem_tile(const MppiParams& p, const MppiState& st, const MppiTerrain& t, size_t other_smem_bytes)
+{
+    DemTile g = { 0, 0, 0, 0 };
+    if (getenv("MPPI_NO_DEM_TILE")) return g;
+    if ((t.grid_size & 3) != 0 || (reinterpret_cast<uintptr_t>(t.dem) & 15) != 0) return g;
+    const float reach = p.dt * fmaxf(fabsf(p.v_max), fabsf(p.v_min)) * (float)p.T;
+    if (!(reach > 0.f) || !(t.resolution > 0.f)) return g;
+    const int hc = (int)(reach / t.resolution) + 4;                         // half extent in cells, 3+ cells of margin
+    const int ic = (int)((st.x + t.half_width) / t.resolution);             // projection_warp.py:39-40
+    const int jc = -(int)((st.y - t.half_width) / t.resolution);
+    int i0 = (ic - hc) & ~3, i1 = ((ic + hc + 2) + 3) & ~3;                // [i0, i1) columns, multiples of 4
+    int j0 = jc - hc, j1 = jc + hc + 2;
+    if (i0 < 0 || j0 < 0 || i1 > t.grid_size || j1 > t.grid_size) return g;
+    const size_t bytes = (size_t)(i1 - i0) * (size_t)(j1 - j0) * sizeof(float);
+    if (bytes + other_smem_bytes > (size_t)227 * 1024) return g;
+    g.i0 = i0; g.j0 = j0; g.w = i1 - i0; g.h = j1 - j0;
+    return g;
+}
+
 static int do_step(MppiHandle* h, const MppiState* state, const MppiState* states_dev, int n_rovers, int proj,
                    const float* noise, uint64_t seed, uint64_t offset, uint32_t k_begin, float* rank_partial,
                    cudaStream_t s, bool to_host = false, bool sharded = false, const LoopCtl* loop = nullptr)
@@ -256,6 +280,8 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     if (to_host) { a.host_cmd = h->cmd_pinned_dev; a.host_seq = ++h->host_seq; }
     if (sharded) { a.peers = h->peers; a.peers.seq = ++h->peers.seq; }
     if (loop) a.loop = *loop;
+    if (h->pipe && state && !states_dev && !loop && n_rovers == 1 && proj == MPPI_PROJ_3D && h->nblocks <= 148)
+        a.tile = plan_dem_tile(h->p, *state, h->terrain, strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks));
     if (h->timing) CK(cudaEventRecord(h->ev0, s));
     cudaError_t e;
     if (h->pipe)

@@ -15,6 +15,8 @@
 #include "mppi_device.cuh"
 
 #include <math_constants.h>
+#include <mutex>
+#include <unordered_set>
 
 namespace mppi {
 namespace MPPI_NS {
@@ -671,6 +673,7 @@ struct PipeSmem {
     float ring_b[kPipeStages][kPipeChunk][8][32];     // x, y, n.xyz, cur.xyz
     float crit[6][32];                                // speed, slope, obs, pf_near, last_x, last_y
     int oob[6][32];
+    unsigned long long tile_bar;                      // completes when the TMA copies of the DEM tile have landed
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -697,6 +700,44 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     }
 }
 
+// TMA bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void tma_load_row(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// projection_warp.py:8-48 on the shared-memory tile (indices proven in range by terrain_window_safe + the tile margins)
+__device__ __forceinline__ Quad corners_tile(const Terr& t, const float* tile, const DemTile& g, float x, float y)
+{
+    int i, j;
+    dem_index(t, x, y, i, j);
+    const float* row = tile + ((j - g.j0) * g.w + (i - g.i0));
+    Quad q;
+    q.q00 = row[0];
+    q.q01 = row[1];
+    q.q10 = row[g.w];
+    q.q11 = row[g.w + 1];
+    return q;
+}
+
+// chain role on the shared-memory DEM tile (3-D projection only)
+template <int PROJ>
+__device__ __forceinline__ void role_chain_tile(const MppiParams& p, const Terr& ter, const float* tile, const DemTile& g,
+                                                float& x, float& y, float3& prev, float v, float sn, float cs, float3& n,
+                                                float& dev)
+{
+    update_position(x, y, prev, v, p.dt, dev);
+    const Quad q = corners_tile(ter, tile, g, x, y);
+    n = normal_on_grid(q, ter.res);
+    const float3 tg = tangent(n, prev);
+    prev = update_orientation_sc(tg, sn, cs, n, dev);
+}
+
 __host__ __device__ inline size_t pipe_smem_offset_floats(int T, int nblocks)
 {
     return (smem_floats(T, kPipeThreads, nblocks) + 3) & ~(size_t)3;      // 16-byte aligned
@@ -718,6 +759,8 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     const int rover = blockIdx.y;
     const Smem s = carve(smem_raw, T, kPipeThreads, A.nblocks);
     PipeSmem& ps = *reinterpret_cast<PipeSmem*>(smem_raw + pipe_smem_offset_floats(T, A.nblocks));
+    float* tile = reinterpret_cast<float*>(reinterpret_cast<char*>(&ps) + ((sizeof(PipeSmem) + 15) & ~(size_t)15));
+    const DemTile tg = A.tile;
     if (tid == 0) {
         trace_stamp(A, 0);
         if (A.trace != nullptr && rover == 0) {
@@ -743,6 +786,9 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             mbar_init(&ps.full_a[i], 32); mbar_init(&ps.empty_a[i], 32);
             mbar_init(&ps.full_b[i], 32); mbar_init(&ps.empty_b[i], 64);
         }
+        mbar_init(&ps.tile_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) trace_stamp(A, 1);
@@ -818,9 +864,13 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             prev = tangent(normal_on_grid(q, ter.res), prev);
         }
         if (lane == 0) trace_stamp(A, 2);
-        // FAST: a full chunk whose cell indices need no clamping (terrain_window_safe) -> no per-step checks at all
-        auto chunk = [&](int c, auto fast_tag) {
+        const bool use_tile = (tg.w > 0) && (PROJ == MPPI_PROJ_3D) && (nfast > 0);
+        if (use_tile) mbar_wait(&ps.tile_bar, 0);
+        // FAST: a full chunk whose cell indices need no clamping (terrain_window_safe) -> no per-step checks at all.
+        // TILE: additionally the four corner gathers read the shared-memory DEM tile.
+        auto chunk = [&](int c, auto fast_tag, auto tile_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
+            constexpr bool TILE = decltype(tile_tag)::value;
             const int sg = c % kPipeStages;
             const unsigned ph = (c / kPipeStages) & 1;
             mbar_wait(&ps.full_a[sg], ph);
@@ -831,7 +881,8 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                 if (FAST || t < T) {
                     const float v = ps.ring_a[sg][i][0][lane];
                     const float sn = ps.ring_a[sg][i][1][lane], cs = ps.ring_a[sg][i][2][lane];
-                    role_chain<PROJ, !FAST>(p, ter, x, y, prev, v, sn, cs, n, oob, dev);
+                    if (TILE) role_chain_tile<PROJ>(p, ter, tile, tg, x, y, prev, v, sn, cs, n, dev);
+                    else role_chain<PROJ, !FAST>(p, ter, x, y, prev, v, sn, cs, n, oob, dev);
                     float* o = &ps.ring_b[sg][i][0][lane];
                     o[0] = x; o[32] = y;
                     if ((i & 1) == 0) {                  // only even steps feed the wheel / slope role
@@ -844,12 +895,21 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             mbar_arrive(&ps.full_b[sg]);
         };
         int c = 0;
-        for (; c < nfast; ++c) chunk(c, FastTag<true>{});
-        for (; c < nchunks; ++c) chunk(c, FastTag<false>{});
+        if (use_tile) { for (; c < nfast; ++c) chunk(c, FastTag<true>{}, FastTag<true>{}); }
+        else { for (; c < nfast; ++c) chunk(c, FastTag<true>{}, FastTag<false>{}); }
+        for (; c < nchunks; ++c) chunk(c, FastTag<false>{}, FastTag<false>{});
         oob += unit_violation(dev);
         if (lane == 0) trace_stamp(A, 3);
     } else if (role == ROLE_WHEELS) {
-        // ---- wheels + slope critic
+        // ---- wheels + slope critic.  Idle while the pipeline fills: this warp first starts the TMA copies of the
+        //      DEM tile (one bulk copy per tile row, 16-byte aligned by construction of the tile geometry).
+        if (tg.w > 0) {
+            if (lane == 0) mbar_expect_tx(&ps.tile_bar, (unsigned)(tg.w * tg.h) * 4u);
+            __syncwarp();
+            for (int r = lane; r < tg.h; r += 32)
+                tma_load_row(tile + (size_t)r * tg.w, tr.dem + ((size_t)(tg.j0 + r) * tr.grid_size + tg.i0),
+                             (unsigned)tg.w * 4u, &ps.tile_bar);
+        }
         float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e;
         float slope = 0.0f;
         auto chunk = [&](int c, auto fast_tag) {
@@ -1114,11 +1174,19 @@ __global__ void mppi_noise_kernel(uint64_t seed, uint64_t offset, uint32_t rover
 // ------------------------------------------------------------------ launchers
 size_t fused_smem_bytes(int T, int block, int nblocks) { return smem_floats(T, block, nblocks) * sizeof(float); }
 
+// Raises the dynamic shared-memory limit of a kernel once (to the 227 KB a CTA may have), not on every launch.
 template <typename Kern>
 static cudaError_t ensure_smem(Kern k, size_t bytes)
 {
-    if (bytes > 48 * 1024) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    return cudaSuccess;
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::unordered_set<const void*> raised;
+    std::lock_guard<std::mutex> lock(mu);
+    const void* key = reinterpret_cast<const void*>(k);
+    if (raised.count(key)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) raised.insert(key);
+    return e;
 }
 
 cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, cudaStream_t s)
@@ -1141,15 +1209,15 @@ cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, 
     return cudaGetLastError();
 }
 
-size_t pipe_smem_bytes(int T, int nblocks)
+size_t pipe_smem_bytes_no_tile(int T, int nblocks)
 {
-    return pipe_smem_offset_floats(T, nblocks) * sizeof(float) + sizeof(PipeSmem);
+    return pipe_smem_offset_floats(T, nblocks) * sizeof(float) + ((sizeof(PipeSmem) + 15) & ~(size_t)15);
 }
 
 cudaError_t launch_fused_pipe(const FusedArgs& a, int proj, int n_rovers, cudaStream_t s)
 {
     const dim3 grid(a.nblocks, n_rovers);
-    const size_t smem = pipe_smem_bytes(a.p.T, a.nblocks);
+    const size_t smem = pipe_smem_bytes_no_tile(a.p.T, a.nblocks) + (size_t)a.tile.w * a.tile.h * sizeof(float);
     cudaError_t e;
 #define MPPI_LAUNCH_PIPE(PROJ, INJ)                                                    \
     do {                                                                               \

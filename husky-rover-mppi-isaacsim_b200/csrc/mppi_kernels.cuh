@@ -44,6 +44,15 @@ struct LoopCtl {
     int32_t iter;                     // index of this iteration (row of `log`)
 };
 
+// Shared-memory DEM tile of the pipelined kernel (latency regime): the square of cells the body can reach, copied
+// once per CTA by TMA bulk copies (one per tile row) while the pipeline fills; the chain warp's four corner gathers
+// per step then hit shared memory (4-byte bank granularity) instead of L1 (128-byte line granularity).  Geometry is
+// computed on the host from the same state the kernel gets.  w == 0: no tile (gathers go through L1 / L2).
+struct DemTile {
+    int32_t i0, j0;                   // DEM column / row of tile element (0, 0); i0 and w are multiples of 4 (16-byte rows)
+    int32_t w, h;                     // tile width / height in cells
+};
+
 struct FusedArgs {
     MppiParams p;
     MppiState state;                  // used when states == nullptr
@@ -70,6 +79,7 @@ struct FusedArgs {
     uint32_t host_seq;                // sequence number stored with the command
     PeerComm peers;                   // sample-sharded multi-GPU exchange (world == 0: off)
     LoopCtl loop;                     // device-resident closed loop (state == nullptr: off)
+    DemTile tile;                     // pipelined kernel only
 };
 
 struct CombineArgs {
@@ -127,6 +137,7 @@ struct SimArgs {
     cudaError_t launch_normalize_test(const float* v, float* out, float* ref, int n, cudaStream_t s);         \
     cudaError_t launch_divsqrt_test(const float* a, const float* b, float* out, float* ref, int n, cudaStream_t s); \
     size_t fused_smem_bytes(int T, int block, int nblocks);                                                    \
+    size_t pipe_smem_bytes_no_tile(int T, int nblocks);                                                        \
     }
 
 MPPI_DECLARE_LAUNCHERS(strict)

@@ -179,68 +179,108 @@ __device__ __forceinline__ int block_compact(bool keep, int idx, float val, int 
 }
 
 // ------------------------------------------------------------------ phase 3: fold partials, finish the update
-// parts: [n][stride] softmax partials (read through L2).  Called by ONE block of >= 64 threads; smem nom1/nom2 hold
-// the old nominal.  `tr`: optional timeline row of this block (see trace_stamp).
+// parts: [n][stride] softmax partials (read through L2).  Called by every thread of ONE block; all but warp 0 return
+// early (at once when n <= 128, after the block-wide scan of the partial headers otherwise): the rest is a few hundred
+// values, where block-wide barriers and reductions would only add latency to the tail of the iteration.
+// smem nom1/nom2 hold the old nominal.  `tr`: optional timeline row (see trace_stamp).
 __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, const float* parts, int n,
                                      const Smem& s, float* nominal1, float* nominal2, float* prev1, float* prev2,
                                      float* opt_v, float* opt_w, float* stats, float* rank_partial,
                                      unsigned oob_count, unsigned nan_count, unsigned long long* tr,
                                      float* host_cmd, unsigned host_seq, const PeerComm* pc = nullptr)
 {
-    const int T = p.T, tid = threadIdx.x, B = blockDim.x;
+    const int T = p.T, lane = threadIdx.x & 31, tid = threadIdx.x, B = blockDim.x;
     const int stride = partial_stride(T);
+    const unsigned FULL = 0xffffffffu;
+    float M = CUDART_INF_F;
+    int arg = 0x7fffffff, cnt = 0;
 
-    // 1. global min / argmin (ties -> lowest sample id)
-    float M = CUDART_INF_F, m_first = CUDART_INF_F;      // m_first: min cost of partial `tid`, reused in step 2
-    int arg = 0x7fffffff;
-    for (int b = tid; b < n; b += B) {
-        const float mb = __ldcg(parts + (size_t)b * stride);
-        const int kb = __float_as_int(__ldcg(parts + (size_t)b * stride + 2));
-        if (b == tid) m_first = mb;
-        pair_min(M, arg, mb, kb);
+    if (n > 128) {
+        // ---- many partials (throughput regime, thousands of blocks): steps 1-2 use the whole block
+        for (int b = tid; b < n; b += B) {
+            const float mb = __ldcg(parts + (size_t)b * stride);
+            const int kb = __float_as_int(__ldcg(parts + (size_t)b * stride + 2));
+            pair_min(M, arg, mb, kb);
+        }
+        block_min(M, arg, s);
+        for (int base = 0; base < n; base += B) {
+            const int b = base + tid;
+            float sc = 0.0f;
+            if (b < n) sc = fexp(fdiv(-(__ldcg(parts + (size_t)b * stride) - M), p.lambda));
+            cnt = block_compact(sc > 0.0f, b, sc, cnt, s);
+        }
+        __syncthreads();
+        if (tid >= 32) return;
+    } else {
+        // ---- few partials (latency regime): one warp, no block barrier anywhere
+        if (tid >= 32) return;
+        // 1. global min / argmin (ties -> lowest sample id); at most four partials per lane
+        float mb4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int b = lane + 32 * q;
+            mb4[q] = CUDART_INF_F;
+            if (b < n) {
+                mb4[q] = __ldcg(parts + (size_t)b * stride);
+                pair_min(M, arg, mb4[q], __float_as_int(__ldcg(parts + (size_t)b * stride + 2)));
+            }
+        }
+        warp_min(M, arg);
+        // 2. scale of every partial relative to M; the non-zero ones are kept, in partial order
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int b = lane + 32 * q;
+            float sc = 0.0f;
+            if (b < n) sc = fexp(fdiv(-(mb4[q] - M), p.lambda));
+            const unsigned keep = __ballot_sync(FULL, sc > 0.0f);
+            if (sc > 0.0f) {
+                const int pos = cnt + __popc(keep & ((1u << lane) - 1u));
+                s.list_i[pos] = b;
+                s.list_w[pos] = sc;
+            }
+            cnt += __popc(keep);
+        }
+        __syncwarp();
     }
-    block_min(M, arg, s);
-    if (tr != nullptr && tid == 0) tr[12] = globaltimer_ns();
+    if (tr != nullptr && lane == 0) tr[12] = globaltimer_ns();
 
-    // 2. scale of every partial relative to M; keep the non-zero ones, in order
-    int cnt = 0;
-    for (int base = 0; base < n; base += B) {
-        const int b = base + tid;
-        float sc = 0.0f;
-        if (b < n) sc = fexp(fdiv(-((base == 0 ? m_first : __ldcg(parts + (size_t)b * stride)) - M), p.lambda));
-        cnt = block_compact(sc > 0.0f, b, sc, cnt, s);
-    }
-    __syncthreads();
-
-    // 3. ordered fold; every thread recomputes S (identical on all threads), thread j < 2T owns column j
+    // 3. ordered fold (one warp from here on).  Every lane accumulates S (identical on all lanes); lane l owns columns
+    //    l, l + 32, ...: eight per pass, all loads of an entry issued together (one L2 round trip per kept partial).
     float S = 0.0f, S2 = 0.0f;
-    for (int col0 = 0; col0 < 2 * T; col0 += 2 * B) {        // two columns per thread and pass: loads overlap
-        const int ca = col0 + tid, cb = ca + B;
-        float acc_a = 0.0f, acc_b = 0.0f;
-        S = 0.0f; S2 = 0.0f;
-#pragma unroll 2
+    for (int col0 = 0; col0 < 2 * T; col0 += 256) {
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.0f;
         for (int e = 0; e < cnt; ++e) {
             const float* pb = parts + (size_t)s.list_i[e] * stride;
             const float sc = s.list_w[e];
-            const float ps = __ldcg(pb + 1), ps2 = __ldcg(pb + 3);
-            const float va = (ca < 2 * T) ? __ldcg(pb + kPartialHeader + ca) : 0.0f;
-            const float vb = (cb < 2 * T) ? __ldcg(pb + kPartialHeader + cb) : 0.0f;
-            S += ps * sc;
-            S2 += ps2 * sc * sc;
-            acc_a += va * sc;
-            acc_b += vb * sc;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = col0 + lane + 32 * q;
+                v[q] = (col < 2 * T) ? __ldcg(pb + kPartialHeader + col) : 0.0f;
+            }
+            if (col0 == 0) {
+                S += __ldcg(pb + 1) * sc;
+                S2 += __ldcg(pb + 3) * sc * sc;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += v[q] * sc;
         }
-        if (ca < 2 * T) s.acc[ca] = acc_a;
-        if (cb < 2 * T) s.acc[cb] = acc_b;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int col = col0 + lane + 32 * q;
+            if (col < 2 * T) s.acc[col] = acc[q];
+        }
     }
-    __syncthreads();
-    if (tr != nullptr && tid == 0) tr[13] = globaltimer_ns();
+    __syncwarp();
+    if (tr != nullptr && lane == 0) tr[13] = globaltimer_ns();
 
-    if (rank_partial != nullptr) {           // sample-sharded mode: publish {M, S, argmin, S2, A1, A2}
-        if (tid == 0) {
+    if (rank_partial != nullptr) {           // sample-sharded mode (NCCL transport): publish {M, S, argmin, S2, A1, A2}
+        if (lane == 0) {
             rank_partial[0] = M; rank_partial[1] = S; rank_partial[2] = __int_as_float(arg); rank_partial[3] = S2;
         }
-        for (int col = tid; col < 2 * T; col += B) rank_partial[kPartialHeader + col] = s.acc[col];
+        for (int col = lane; col < 2 * T; col += 32) rank_partial[kPartialHeader + col] = s.acc[col];
         return;
     }
 
@@ -251,15 +291,15 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         const size_t slot = ((size_t)(seq & 1u) * world + me) * stride;
         for (int r = 0; r < world; ++r) {                  // NVLink stores (plain local stores for r == me)
             float* dst = pc->x[r] + slot;
-            if (tid == 0) { dst[0] = M; dst[1] = S; dst[2] = __int_as_float(arg); dst[3] = S2; }
-            for (int col = tid; col < 2 * T; col += B) dst[kPartialHeader + col] = s.acc[col];
+            if (lane == 0) { dst[0] = M; dst[1] = S; dst[2] = __int_as_float(arg); dst[3] = S2; }
+            for (int col = lane; col < 2 * T; col += 32) dst[kPartialHeader + col] = s.acc[col];
         }
-        // the barrier orders every thread's stores before the system-scope release of the flags below
-        __syncthreads();
-        if (tid < world) {
-            unsigned int* theirs = pc->f[tid] + (seq & 1u) * world + me;
+        // __syncwarp orders every lane's stores before the system-scope release of the flags below
+        __syncwarp();
+        if (lane < world) {
+            unsigned int* theirs = pc->f[lane] + (seq & 1u) * world + me;
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
-            const unsigned int* mine = pc->f[me] + (seq & 1u) * world + tid;
+            const unsigned int* mine = pc->f[me] + (seq & 1u) * world + lane;
             unsigned got;
             for (unsigned spin = 0;; ++spin) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
@@ -268,7 +308,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
                 if (spin > (1u << 24)) __trap();           // a missing rank must fail loudly, never hang the GPU
             }
         }
-        __syncthreads();
+        __syncwarp();
         combine_and_finalize(p, st, pc->x[me] + (size_t)(seq & 1u) * world * stride, world, s, nominal1, nominal2,
                              prev1, prev2, opt_v, opt_w, stats, nullptr, oob_count, nan_count, nullptr, host_cmd,
                              host_seq, nullptr);
@@ -280,7 +320,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
     {
         const Recip rS = make_recip(S);
         const float oma = 1.0f - p.opt_a;
-        for (int col = tid; col < 2 * T; col += B) {
+        for (int col = lane; col < 2 * T; col += 32) {
             const float nv = fdiv(s.acc[col], rS);
             const float drive = nv * p.opt_k * oma;
             s.acc[col] = nv;
@@ -288,12 +328,12 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
             else { prev2[col - T] = s.nom2[col - T]; nominal2[col - T] = nv; s.nom2[col - T] = drive; }
         }
     }
-    __syncthreads();
-    if (tr != nullptr && tid == 0) tr[14] = globaltimer_ns();
+    __syncwarp();
+    if (tr != nullptr && lane == 0) tr[14] = globaltimer_ns();
 
     if (p.input_model == MPPI_INPUT_UNICYCLE) {
         // velocity-space model: the weighted (v, w) sequence is the optimal velocity sequence (s.acc holds it)
-        for (int t = tid; t < T; t += B) {
+        for (int t = lane; t < T; t += 32) {
             const float v = s.acc[t], w = s.acc[T + t];
             opt_v[t] = v; opt_w[t] = w;
             if (t == 0) {
@@ -302,26 +342,17 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
                     *reinterpret_cast<float4*>(host_cmd) = make_float4(v, w, __uint_as_float(host_seq), 0.0f);
             }
         }
-        if (tid == 0) {
-            stats[0] = M; stats[1] = __int_as_float(arg); stats[2] = S;
-            stats[3] = __uint_as_float(oob_count); stats[4] = __uint_as_float(nan_count);
-            stats[5] = fdiv(S * S, S2);
-        }
-        return;
-    }
-
-    // 5. optimal sequence -> (v*, w*) with (opt_k, opt_a) (MPPI_isaac.py:672-692).  The two wheel recurrences
-    //    l <- l a + drive_l[t], r <- r a + drive_r[t] are the only sequential part: one lane of warp 0 runs the left
-    //    wheel and one lane of warp 1 the right wheel, then all threads map (l, r) -> (v, w) in parallel.  Same
-    //    operations in the same order as a one-thread loop.
-    {
-        const int right_tid = (B >= 64) ? 32 : 0;        // a second warp when there is one
-        for (int side = 0; side < 2; ++side) {
-            if (tid != (side == 0 ? 0 : right_tid)) continue;
-            float* d = (side == 0) ? s.nom1 : s.nom2;
-            float x = (side == 0) ? st.wheel_l : st.wheel_r;
-            constexpr int N = 8;                         // steps per register batch; the next batch is loaded
-            float cur[N], nxt[N];                        // BEFORE the current one is stored (in place)
+    } else {
+        // 5. optimal sequence -> (v*, w*) with (opt_k, opt_a) (MPPI_isaac.py:672-692).  The two wheel recurrences
+        //    l <- l a + drive_l[t], r <- r a + drive_r[t] are the only sequential part: lane 0 runs the left wheel and
+        //    lane 1 the right wheel in the same instruction stream, in register batches whose successor is loaded
+        //    before the batch is stored in place; then all lanes map (l, r) -> (v, w).  Same operations in the same
+        //    order as a one-thread loop.
+        if (lane < 2) {
+            float* d = (lane == 0) ? s.nom1 : s.nom2;
+            float x = (lane == 0) ? st.wheel_l : st.wheel_r;
+            constexpr int N = 8;
+            float cur[N], nxt[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) cur[i] = (i < T) ? d[i] : 0.0f;
             for (int t0 = 0; t0 < T; t0 += N) {
@@ -335,11 +366,9 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
                 for (int i = 0; i < N; ++i) cur[i] = nxt[i];
             }
         }
-    }
-    __syncthreads();
-    {
+        __syncwarp();
         const Recip rw = make_recip(p.r_wheels);
-        for (int t = tid; t < T; t += B) {
+        for (int t = lane; t < T; t += 32) {
             const float l = s.nom1[t], r = s.nom2[t];
             const float v = clampf((l + r) / 2.0f, p.v_min, p.v_max);
             const float w = clampf(fdiv(-l + r, rw), p.w_min, p.w_max);
@@ -353,7 +382,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
             }
         }
     }
-    if (tid == 0) {
+    if (lane == 0) {
         stats[0] = M;
         stats[1] = __int_as_float(arg);
         stats[2] = S;
@@ -361,7 +390,8 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         stats[4] = __uint_as_float(nan_count);
         stats[5] = fdiv(S * S, S2);           // effective sample size
     }
-    if (tr != nullptr && tid == 0) tr[15] = globaltimer_ns();
+    __syncwarp();
+    if (tr != nullptr && lane == 0) tr[15] = globaltimer_ns();
 }
 
 // ------------------------------------------------------------------ closed loop: the plant step (one thread)

@@ -3,6 +3,8 @@
 // that computes needs a CUDA device and fails with MPPI_ERR_CUDA otherwise.
 #include "mppi_kernels.cuh"
 
+#include <cuda.h>
+
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
@@ -42,6 +44,9 @@ struct MppiHandle {
     int32_t* loop_ctl;           // device {iterations done, goal reached}
     float* loop_log;             // device [loop_log_cap][8]
     int32_t loop_log_cap;
+    // TMA descriptor of the DEM for the pipelined kernel's shared-memory tile, re-encoded when its key changes
+    TmaDesc dem_desc;
+    const float* desc_dem; int desc_gs, desc_w, desc_h; bool desc_ok;
 };
 
 static thread_local char g_cuda_err[256];
@@ -241,13 +246,43 @@ static DemTile plan_dem_tile(const MppiParams& p, const MppiState& st, const Mpp
     const int hc = (int)(reach / t.resolution) + 4;                         // half extent in cells, 3+ cells of margin
     const int ic = (int)((st.x + t.half_width) / t.resolution);             // projection_warp.py:39-40
     const int jc = -(int)((st.y - t.half_width) / t.resolution);
-    int i0 = (ic - hc) & ~3, i1 = ((ic + hc + 2) + 3) & ~3;                // [i0, i1) columns, multiples of 4
-    int j0 = jc - hc, j1 = jc + hc + 2;
-    if (i0 < 0 || j0 < 0 || i1 > t.grid_size || j1 > t.grid_size) return g;
-    const size_t bytes = (size_t)(i1 - i0) * (size_t)(j1 - j0) * sizeof(float);
+    // box of constant size for given parameters (the TMA descriptor holds it): columns [i0, i0 + w) with i0 a multiple of
+    // 4 and w = 2 hc + 8 covers ic - hc .. ic + hc + 1 for every alignment of ic
+    const int w = (2 * hc + 2 + 3 + 3) & ~3, hgt = 2 * hc + 2;
+    const int i0 = (ic - hc) & ~3, j0 = jc - hc;
+    if (w > 256 || hgt > 256 || i0 < 0 || j0 < 0 || i0 + w > t.grid_size || j0 + hgt > t.grid_size) return g;
+    const size_t bytes = (size_t)w * (size_t)hgt * sizeof(float);
     if (bytes + other_smem_bytes > (size_t)227 * 1024) return g;
-    g.i0 = i0; g.j0 = j0; g.w = i1 - i0; g.h = j1 - j0;
+    g.i0 = i0; g.j0 = j0; g.w = w; g.h = hgt;
     return g;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link against libcuda).
+static bool encode_dem_desc(MppiHandle* h, const MppiTerrain& t, int w, int hgt)
+{
+    if (h->desc_ok && h->desc_dem == t.dem && h->desc_gs == t.grid_size && h->desc_w == w && h->desc_h == hgt) return true;
+    h->desc_ok = false;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+        fn = reinterpret_cast<EncodeFn>(p);
+    }
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap is 128 bytes");
+    const cuuint64_t gdim[2] = { (cuuint64_t)t.grid_size, (cuuint64_t)t.grid_size };
+    const cuuint64_t gstride[1] = { (cuuint64_t)t.grid_size * sizeof(float) };
+    const cuuint32_t box[2] = { (cuuint32_t)w, (cuuint32_t)hgt };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(&h->dem_desc), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<float*>(t.dem), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    h->desc_dem = t.dem; h->desc_gs = t.grid_size; h->desc_w = w; h->desc_h = hgt; h->desc_ok = true;
+    return true;
 }
 
 static int do_step(MppiHandle* h, const MppiState* state, const MppiState* states_dev, int n_rovers, int proj,
@@ -281,7 +316,13 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     if (sharded) { a.peers = h->peers; a.peers.seq = ++h->peers.seq; }
     if (loop) a.loop = *loop;
     if (h->pipe && state && !states_dev && !loop && n_rovers == 1 && proj == MPPI_PROJ_3D && h->nblocks <= 148)
+    {
         a.tile = plan_dem_tile(h->p, *state, h->terrain, strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks));
+        if (a.tile.w > 0) {
+            if (encode_dem_desc(h, h->terrain, a.tile.w, a.tile.h)) a.dem_desc = h->dem_desc;
+            else a.tile.w = a.tile.h = 0;
+        }
+    }
     if (h->timing) CK(cudaEventRecord(h->ev0, s));
     cudaError_t e;
     if (h->pipe)

@@ -730,11 +730,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     }
 }
 
-// TMA bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
-__device__ __forceinline__ void tma_load_row(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar)
+// TMA tensor copy global -> shared: ONE instruction moves the whole w x h box of the 2-D DEM tensor described by
+// `desc` whose corner is (column c0, row c1); completion (bytes) is counted on `bar`.  (Row-by-row 1-D bulk copies were
+// tried first: the TMA unit spends ~46 cycles per request, 186 rows cost ~4 us.)
+__device__ __forceinline__ void tma_load_tile_2d(void* dst_smem, const TmaDesc* desc, int c0, int c1, unsigned long long* bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(desc), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
 {
@@ -770,14 +772,14 @@ __device__ __forceinline__ void role_chain_tile(const MppiParams& p, const Terr&
 
 __host__ __device__ inline size_t pipe_smem_offset_floats(int T, int nblocks)
 {
-    return (smem_floats(T, kPipeThreads, nblocks) + 3) & ~(size_t)3;      // 16-byte aligned
+    return (smem_floats(T, kPipeThreads, nblocks) + 31) & ~(size_t)31;    // 128-byte aligned (TMA destination follows)
 }
 
 template <int PROJ, bool INJECT>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
 {
-    extern __shared__ __align__(16) float smem_raw[];
+    extern __shared__ __align__(128) float smem_raw[];
     const MppiParams& p = A.p;
     const int T = p.T, K = p.K, tid = threadIdx.x;
     const int lane = tid & 31;
@@ -789,7 +791,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     const int rover = blockIdx.y;
     const Smem s = carve(smem_raw, T, kPipeThreads, A.nblocks);
     PipeSmem& ps = *reinterpret_cast<PipeSmem*>(smem_raw + pipe_smem_offset_floats(T, A.nblocks));
-    float* tile = reinterpret_cast<float*>(reinterpret_cast<char*>(&ps) + ((sizeof(PipeSmem) + 15) & ~(size_t)15));
+    float* tile = reinterpret_cast<float*>(reinterpret_cast<char*>(&ps) + ((sizeof(PipeSmem) + 127) & ~(size_t)127));
     const DemTile tg = A.tile;
     if (tid == 0) {
         trace_stamp(A, 0);
@@ -809,7 +811,6 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
 
     float* nominal1 = A.nominal1 + (size_t)rover * T;
     float* nominal2 = A.nominal2 + (size_t)rover * T;
-    for (int t = tid; t < T; t += kPipeThreads) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
     if (tid == 0) {
         for (int i = 0; i < kPipeStages; ++i) {
             mbar_init(&ps.full_u[i], 32); mbar_init(&ps.empty_u[i], 32);
@@ -819,7 +820,14 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         mbar_init(&ps.tile_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // The TMA copy of the DEM tile starts before the block even synchronises, so that the tile lands while the
+        // nominal is loaded and the noise / filter stages fill the pipeline.
+        if (tg.w > 0) {
+            mbar_expect_tx(&ps.tile_bar, (unsigned)(tg.w * tg.h) * 4u);
+            tma_load_tile_2d(tile, &A.dem_desc, tg.i0, tg.j0, &ps.tile_bar);
+        }
     }
+    for (int t = tid; t < T; t += kPipeThreads) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
     __syncthreads();
     if (tid == 0) trace_stamp(A, 1);
 
@@ -931,15 +939,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         oob += unit_violation(dev);
         if (lane == 0) trace_stamp(A, 3);
     } else if (role == ROLE_WHEELS) {
-        // ---- wheels + slope critic.  Idle while the pipeline fills: this warp first starts the TMA copies of the
-        //      DEM tile (one bulk copy per tile row, 16-byte aligned by construction of the tile geometry).
-        if (tg.w > 0) {
-            if (lane == 0) mbar_expect_tx(&ps.tile_bar, (unsigned)(tg.w * tg.h) * 4u);
-            __syncwarp();
-            for (int r = lane; r < tg.h; r += 32)
-                tma_load_row(tile + (size_t)r * tg.w, tr.dem + ((size_t)(tg.j0 + r) * tr.grid_size + tg.i0),
-                             (unsigned)tg.w * 4u, &ps.tile_bar);
-        }
+        // ---- wheels + slope critic
         float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e;
         float slope = 0.0f;
         auto chunk = [&](int c, auto fast_tag) {
@@ -1241,7 +1241,7 @@ cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, 
 
 size_t pipe_smem_bytes_no_tile(int T, int nblocks)
 {
-    return pipe_smem_offset_floats(T, nblocks) * sizeof(float) + ((sizeof(PipeSmem) + 15) & ~(size_t)15);
+    return pipe_smem_offset_floats(T, nblocks) * sizeof(float) + ((sizeof(PipeSmem) + 127) & ~(size_t)127);
 }
 
 cudaError_t launch_fused_pipe(const FusedArgs& a, int proj, int n_rovers, cudaStream_t s)

@@ -50,8 +50,12 @@ struct LoopCtl {
 // computed on the host from the same state the kernel gets.  w == 0: no tile (gathers go through L1 / L2).
 struct DemTile {
     int32_t i0, j0;                   // DEM column / row of tile element (0, 0); i0 and w are multiples of 4 (16-byte rows)
-    int32_t w, h;                     // tile width / height in cells
+    int32_t w, h;                     // tile width / height in cells (the box of the TMA descriptor)
 };
+
+// 128-byte TMA descriptor (CUtensorMap) of the DEM as a 2-D fp32 tensor with a w x h box, encoded on the host
+// (cuTensorMapEncodeTiled) whenever the terrain or the box changes; opaque to the device code.
+struct alignas(64) TmaDesc { unsigned long long opaque[16]; };
 
 struct FusedArgs {
     MppiParams p;
@@ -80,6 +84,7 @@ struct FusedArgs {
     PeerComm peers;                   // sample-sharded multi-GPU exchange (world == 0: off)
     LoopCtl loop;                     // device-resident closed loop (state == nullptr: off)
     DemTile tile;                     // pipelined kernel only
+    TmaDesc dem_desc;                 // valid when tile.w > 0
 };
 
 struct CombineArgs {

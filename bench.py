@@ -119,7 +119,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     w, dem, cm, start, goal = build_workload(args.workload, args.K, args.T)
-    base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=args.warmup)
+    base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=max(5, args.warmup))
     line = {
         "impl": "reference", "metric": "MPPI sample-steps/s", "value": base["value"], "unit": "sample-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],

@@ -233,10 +233,11 @@ extern "C" int mppi_get_nominal(MppiHandle* h, float* u1, float* u2, int32_t n_r
     return MPPI_OK;
 }
 
-// Geometry of the shared-memory DEM tile of the pipelined kernel (DemTile in mppi_kernels.cuh): the cells the body can
-// reach in T steps plus a margin, with 16-byte aligned rows for the TMA bulk copies.  Returns w = 0 (no tile) when the
-// tile would not fit beside the pipeline's rings, the rows cannot be aligned, or the window touches the map border.
-static DemTile plan_dem_tile(const MppiParams& p, const MppiState& st, const MppiTerrain& t, size_t other_smem_bytes)
+// Box of the shared-memory DEM tile of the pipelined kernel (DemTile in mppi_kernels.cuh): the cells the body can reach
+// in T steps plus a margin, rows a multiple of 16 bytes for the TMA tensor copy.  The box depends on the parameters and
+// the map only; the kernel places its corner around the robot.  Returns w = 0 (no tile) when the tile would not fit
+// beside the pipeline's rings or the rows cannot be aligned.
+static DemTile plan_dem_tile(const MppiParams& p, const MppiTerrain& t, size_t other_smem_bytes)
 {
     DemTile g = { 0, 0, 0, 0 };
     if (getenv("MPPI_NO_DEM_TILE")) return g;
@@ -244,16 +245,11 @@ static DemTile plan_dem_tile(const MppiParams& p, const MppiState& st, const Mpp
     const float reach = p.dt * fmaxf(fabsf(p.v_max), fabsf(p.v_min)) * (float)p.T;
     if (!(reach > 0.f) || !(t.resolution > 0.f)) return g;
     const int hc = (int)(reach / t.resolution) + 4;                         // half extent in cells, 3+ cells of margin
-    const int ic = (int)((st.x + t.half_width) / t.resolution);             // projection_warp.py:39-40
-    const int jc = -(int)((st.y - t.half_width) / t.resolution);
-    // box of constant size for given parameters (the TMA descriptor holds it): columns [i0, i0 + w) with i0 a multiple of
-    // 4 and w = 2 hc + 8 covers ic - hc .. ic + hc + 1 for every alignment of ic
+    // columns [i0, i0 + w) with i0 = (ic - hc) rounded down to a multiple of 4: w = 2 hc + 8 covers ic - hc .. ic + hc + 1
     const int w = (2 * hc + 2 + 3 + 3) & ~3, hgt = 2 * hc + 2;
-    const int i0 = (ic - hc) & ~3, j0 = jc - hc;
-    if (w > 256 || hgt > 256 || i0 < 0 || j0 < 0 || i0 + w > t.grid_size || j0 + hgt > t.grid_size) return g;
-    const size_t bytes = (size_t)w * (size_t)hgt * sizeof(float);
-    if (bytes + other_smem_bytes > (size_t)227 * 1024) return g;
-    g.i0 = i0; g.j0 = j0; g.w = w; g.h = hgt;
+    if (w > 256 || hgt > 256 || w > t.grid_size || hgt > t.grid_size) return g;
+    if ((size_t)w * (size_t)hgt * sizeof(float) + other_smem_bytes > (size_t)227 * 1024) return g;
+    g.w = w; g.h = hgt;
     return g;
 }
 
@@ -315,9 +311,9 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     if (to_host) { a.host_cmd = h->cmd_pinned_dev; a.host_seq = ++h->host_seq; }
     if (sharded) { a.peers = h->peers; a.peers.seq = ++h->peers.seq; }
     if (loop) a.loop = *loop;
-    if (h->pipe && state && !states_dev && !loop && n_rovers == 1 && proj == MPPI_PROJ_3D && h->nblocks <= 148)
+    if (h->pipe && !states_dev && n_rovers == 1 && proj == MPPI_PROJ_3D && h->nblocks <= 148)
     {
-        a.tile = plan_dem_tile(h->p, *state, h->terrain, strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks));
+        a.tile = plan_dem_tile(h->p, h->terrain, strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks));
         if (a.tile.w > 0) {
             if (encode_dem_desc(h, h->terrain, a.tile.w, a.tile.h)) a.dem_desc = h->dem_desc;
             else a.tile.w = a.tile.h = 0;

@@ -792,7 +792,6 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     const Smem s = carve(smem_raw, T, kPipeThreads, A.nblocks);
     PipeSmem& ps = *reinterpret_cast<PipeSmem*>(smem_raw + pipe_smem_offset_floats(T, A.nblocks));
     float* tile = reinterpret_cast<float*>(reinterpret_cast<char*>(&ps) + ((sizeof(PipeSmem) + 127) & ~(size_t)127));
-    const DemTile tg = A.tile;
     if (tid == 0) {
         trace_stamp(A, 0);
         if (A.trace != nullptr && rover == 0) {
@@ -808,6 +807,19 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     const Terr ter = make_terr(tr);
     const SampleConsts sc = make_consts(p, st);
     const NoiseKey nk = make_noise_key(A.seed, A.offset, (uint32_t)rover);
+    // DEM tile: the host fixes the box (w x h, part of the TMA descriptor); its corner follows the robot, which may
+    // live in device memory (closed loop), so it is placed here with the same index formula as the gathers
+    DemTile tg = A.tile;
+    if (tg.w > 0) {
+        const int hc = (tg.h - 2) / 2;
+        int ic, jc;
+        dem_index(ter, st.x, st.y, ic, jc);
+        tg.i0 = (ic - hc) & ~3;
+        tg.j0 = jc - hc;
+        if (!terrain_window_safe(p, st, tr) || tg.i0 < 0 || tg.j0 < 0 || tg.i0 + tg.w > tr.grid_size ||
+            tg.j0 + tg.h > tr.grid_size)
+            tg.w = 0;
+    }
 
     float* nominal1 = A.nominal1 + (size_t)rover * T;
     float* nominal2 = A.nominal2 + (size_t)rover * T;

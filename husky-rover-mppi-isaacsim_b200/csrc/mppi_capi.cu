@@ -242,7 +242,8 @@ static DemTile plan_dem_tile(const MppiParams& p, const MppiTerrain& t, size_t o
     DemTile g = { 0, 0, 0, 0 };
     if (getenv("MPPI_NO_DEM_TILE")) return g;
     if ((t.grid_size & 3) != 0 || (reinterpret_cast<uintptr_t>(t.dem) & 15) != 0) return g;
-    const float reach = p.dt * fmaxf(fabsf(p.v_max), fabsf(p.v_min)) * (float)p.T;
+    // body reach + the lateral wheel offset: the wheel role reads its two nearest-cell heights from the tile too
+    const float reach = p.dt * fmaxf(fabsf(p.v_max), fabsf(p.v_min)) * (float)p.T + fabsf(p.wheel_offset);
     if (!(reach > 0.f) || !(t.resolution > 0.f)) return g;
     const int hc = (int)(reach / t.resolution) + 4;                         // half extent in cells, 3+ cells of margin
     // columns [i0, i0 + w) with i0 = (ic - hc) rounded down to a multiple of 4: w = 2 hc + 8 covers ic - hc .. ic + hc + 1

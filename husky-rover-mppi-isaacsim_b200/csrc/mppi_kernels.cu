@@ -954,8 +954,11 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         // ---- wheels + slope critic
         float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e;
         float slope = 0.0f;
-        auto chunk = [&](int c, auto fast_tag) {
+        const bool use_tile = (tg.w > 0) && (PROJ == MPPI_PROJ_3D) && (nfast > 0);
+        if (use_tile) mbar_wait(&ps.tile_bar, 0);
+        auto chunk = [&](int c, auto fast_tag, auto tile_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
+            constexpr bool TILE = decltype(tile_tag)::value;
             const int sg = c % kPipeStages;
             mbar_wait(&ps.full_b[sg], (c / kPipeStages) & 1);
 #pragma unroll
@@ -963,15 +966,17 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                 const int t = c * kPipeChunk + i;
                 if (FAST || t < T) {
                     const float* o = &ps.ring_b[sg][i][0][lane];
-                    role_wheels<PROJ, !FAST>(p, ter, t, o[0], o[32], make_float3(o[64], o[96], o[128]),
-                                             make_float3(o[160], o[192], o[224]), lw_e, rw_e, slope, oob);
+                    role_wheels<PROJ, !FAST, TILE>(p, ter, t, o[0], o[32], make_float3(o[64], o[96], o[128]),
+                                                   make_float3(o[160], o[192], o[224]), lw_e, rw_e, slope, oob,
+                                                   tile, tg.w, tg.i0, tg.j0);
                 }
             }
             mbar_arrive(&ps.empty_b[sg]);
         };
         int c = 0;
-        for (; c < nfast; ++c) chunk(c, FastTag<true>{});
-        for (; c < nchunks; ++c) chunk(c, FastTag<false>{});
+        if (use_tile) { for (; c < nfast; ++c) chunk(c, FastTag<true>{}, FastTag<true>{}); }
+        else { for (; c < nfast; ++c) chunk(c, FastTag<true>{}, FastTag<false>{}); }
+        for (; c < nchunks; ++c) chunk(c, FastTag<false>{}, FastTag<false>{});
         ps.crit[1][lane] = slope;
     } else {
         // ---- obstacle + near-goal path critic + last point.  This warp idles while the pipeline fills: it first

@@ -31,7 +31,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 // slot: 0 entry, 1 set-up done, 2 rollout start, 3 rollout end, 4 all roles joined, 5 partial published,
 //       6 update finished (last block only), 7 SM id, 8 cost ready, 9 block min, 10 block sum + compaction,
 //       11 ticket taken, 12..15 last block: global min, ordered fold, nominal written, (v*, w*) written
-constexpr int kTraceSlots = 16;
+constexpr int kTraceSlots = 32;       // 16..31: SM-clock stamps inside the last block's update (cycles)
 __device__ __forceinline__ void trace_stamp(const FusedArgs& A, int slot)
 {
     if (A.trace != nullptr && blockIdx.y == 0) A.trace[(size_t)blockIdx.x * kTraceSlots + slot] = globaltimer_ns();
@@ -194,6 +194,8 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
     const unsigned FULL = 0xffffffffu;
     float M = CUDART_INF_F;
     int arg = 0x7fffffff, cnt = 0;
+#define MPPI_CLK(slot) do { if (tr != nullptr && (threadIdx.x & 31) == 0 && threadIdx.x < 32) tr[slot] = (unsigned long long)clock64(); } while (0)
+    MPPI_CLK(16);
 
     if (n > 128) {
         // ---- many partials (throughput regime, thousands of blocks): steps 1-2 use the whole block
@@ -226,6 +228,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
             }
         }
         warp_min(M, arg);
+        MPPI_CLK(17);
         // 2. scale of every partial relative to M; the non-zero ones are kept, in partial order
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -241,6 +244,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
             cnt += __popc(keep);
         }
         __syncwarp();
+        MPPI_CLK(18);
     }
     if (tr != nullptr && lane == 0) tr[12] = globaltimer_ns();
 
@@ -274,6 +278,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         }
     }
     __syncwarp();
+    MPPI_CLK(19);
     if (tr != nullptr && lane == 0) tr[13] = globaltimer_ns();
 
     if (rank_partial != nullptr) {           // sample-sharded mode (NCCL transport): publish {M, S, argmin, S2, A1, A2}
@@ -329,6 +334,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         }
     }
     __syncwarp();
+    MPPI_CLK(20);
     if (tr != nullptr && lane == 0) tr[14] = globaltimer_ns();
 
     if (p.input_model == MPPI_INPUT_UNICYCLE) {
@@ -367,6 +373,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
             }
         }
         __syncwarp();
+        MPPI_CLK(21);
         const Recip rw = make_recip(p.r_wheels);
         for (int t = lane; t < T; t += 32) {
             const float l = s.nom1[t], r = s.nom2[t];
@@ -391,7 +398,9 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         stats[5] = fdiv(S * S, S2);           // effective sample size
     }
     __syncwarp();
+    MPPI_CLK(22);
     if (tr != nullptr && lane == 0) tr[15] = globaltimer_ns();
+#undef MPPI_CLK
 }
 
 // ------------------------------------------------------------------ closed loop: the plant step (one thread)
@@ -548,6 +557,7 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
     // publish: the barrier orders every thread's partial stores before thread 0's gpu-scope release
     __syncthreads();
     if (tid == 0) {
+        if (A.trace != nullptr && rover == 0) A.trace[(size_t)blockIdx.x * kTraceSlots + 24] = (unsigned long long)clock64();
         unsigned ticket;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;"
                      : "=r"(ticket) : "l"(&A.counters[rover * kCounterStride + 0]) : "memory");
@@ -558,6 +568,7 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
     if (!s.red_i[63]) return;
     // every partial was published before its block's fence + ticket; the reads below go to L2 (__ldcg)
 
+    if (A.trace != nullptr && rover == 0 && tid == 0) A.trace[(size_t)blockIdx.x * kTraceSlots + 23] = (unsigned long long)clock64();
     const unsigned oob_count = __ldcg(&A.counters[rover * kCounterStride + 1]);
     const unsigned nan_count = __ldcg(&A.counters[rover * kCounterStride + 2]);
     combine_and_finalize(p, st, A.partials + (size_t)rover * A.nblocks * stride, A.nblocks, s,

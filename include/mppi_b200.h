@@ -254,10 +254,11 @@ int mppi_get_outputs(MppiHandle *h, MppiOutputs *out);
 int mppi_enable_timing(MppiHandle *h, int32_t on);
 int mppi_last_step_us(MppiHandle *h, float *us);
 
-/* Profiling aid: when trace_dev != NULL every block of rover 0 stores eight 64-bit words per step
- * {entry, set-up done, rollout start, rollout end, roles joined, partial published, update finished (last block
- * only), SM id}; the first seven are %globaltimer nanoseconds.  trace_dev: device [nblocks * 8] uint64 (nblocks is
- * returned through nblocks_out); NULL switches the stamps off (default). */
+/* Profiling aid: when trace_dev != NULL every block of rover 0 stores 32 64-bit words per step: slots 0-6 and 8-15
+ * are %globaltimer nanoseconds of the kernel's phases (entry, set-up done, rollout start / end, roles joined, partial
+ * published, update finished, cost ready, block softmax, ticket, and the last block's update phases), slot 7 the SM id,
+ * slots 16-24 SM-clock stamps inside the last block's update (tools/timeline.py decodes them).  trace_dev: device
+ * [nblocks * 32] uint64 (nblocks is returned through nblocks_out); NULL switches the stamps off (default). */
 int mppi_set_trace(MppiHandle *h, uint64_t *trace_dev, int32_t *nblocks_out);
 
 /* Test hook: evaluates the specified ("det") math on the device. fn: 0 sincos, 1 sincos(2*pi*u), 2 log, 3 exp.

@@ -21,8 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 PHASES = ["entry", "setup_done", "rollout_start", "rollout_end", "roles_joined", "partial_published", "update_done", "smid",
-          "cost_ready", "block_min", "block_sum_compact", "ticket", "g_min", "g_fold", "g_nominal", "g_cmd"]
-NS = 16
+          "cost_ready", "block_min", "block_sum_compact", "ticket", "g_min", "g_fold", "g_nominal", "g_cmd"] + ["smid"] * 16
+NS = 32
 
 
 def main():
@@ -60,7 +60,7 @@ def main():
     for i in range(5):
         core.step(st, capi.PROJ_3D, None, 42, i)
     torch.cuda.synchronize()
-    rows, evt, raw_rows = [], [], []
+    rows, evt, raw_rows, clk_rows = [], [], [], []
     for i in range(a.reps):
         if not a.no_flush:
             flush.fill_(i & 255)
@@ -78,6 +78,7 @@ def main():
         rel[:, 7] = t[:, 7]
         rows.append(rel)
         raw_rows.append(rel)
+        clk_rows.append(t.copy())
     if a.dump:
         np.save(a.dump, np.stack(raw_rows))
     rel = np.stack(rows)                                  # [reps, nblocks, 7]
@@ -93,6 +94,20 @@ def main():
         out["phases_us"][name] = {"first": float(np.nanmedian(np.nanmin(x, axis=1))),
                                   "median": float(np.nanmedian(x)),
                                   "last": float(np.nanmedian(np.nanmax(x, axis=1)))}
+    # SM-clock stamps of the last block's update (cycles since its ticket was requested)
+    raw = np.stack(clk_rows)                              # [reps, nblocks, 32]
+    cyc = {}
+    names = {23: "ticket_known", 16: "enter_update", 17: "min_done", 18: "scales_compacted", 19: "fold_done",
+             20: "nominal_done", 21: "recurrence_done", 22: "outputs_done"}
+    for slot, name in names.items():
+        vals = []
+        for r in range(raw.shape[0]):
+            b = int(np.argmax(raw[r, :, 22]))             # the block that ran the update
+            if raw[r, b, 22] > 0 and raw[r, b, slot] > 0:
+                vals.append(raw[r, b, slot] - raw[r, b, 24])
+        if vals:
+            cyc[name] = float(np.median(vals))
+    out["last_block_update_cycles"] = cyc
     dur = rel[:, :, 3] - rel[:, :, 2]
     out["rollout_us_per_block"] = {"min": float(np.nanmin(dur)), "median": float(np.nanmedian(dur)),
                                    "max": float(np.nanmax(dur)), "per_step_ns_median": float(np.nanmedian(dur) * 1e3 / w.T)}

@@ -559,7 +559,11 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
     if (tid == 0) {
         if (A.trace != nullptr && rover == 0) A.trace[(size_t)blockIdx.x * kTraceSlots + 24] = (unsigned long long)clock64();
         unsigned ticket;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;"
+        // release only: the partials of this block are ordered before the ticket.  The last block reads the other
+        // blocks' partials with ld.global STRONG.GPU loads issued after (and control-dependent on) the ticket value,
+        // straight from L2 where every released partial already is -- an acquire here would only add an L1
+        // invalidation (CCTL.IVALL) to the tail of every block.
+        asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;"
                      : "=r"(ticket) : "l"(&A.counters[rover * kCounterStride + 0]) : "memory");
         s.red_i[63] = (ticket == (unsigned)(A.nblocks - 1));
         trace_stamp(A, 11);

@@ -39,6 +39,7 @@ struct MppiHandle {
     void* comm_local;            // this rank's exchange allocation: [2][world][stride] floats + [2][world] flags
     void* comm_peer[kMaxRanks];  // peers' allocations opened with CUDA IPC (nullptr for this rank)
     PeerComm peers;
+    int comm_nblocks;            // blocks per rank the exchange buffers were laid out for
     // device-resident closed loop (mppi_run_closed_loop)
     MppiState* loop_state;       // device
     int32_t* loop_ctl;           // device {iterations done, goal reached}
@@ -314,7 +315,8 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     if (loop) a.loop = *loop;
     if (h->pipe && !states_dev && n_rovers == 1 && proj == MPPI_PROJ_3D && h->nblocks <= 148)
     {
-        a.tile = plan_dem_tile(h->p, h->terrain, strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks));
+        a.tile = plan_dem_tile(h->p, h->terrain,
+                               strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks * (a.peers.world > 0 ? a.peers.world : 1)));
         if (a.tile.w > 0) {
             if (encode_dem_desc(h, h->terrain, a.tile.w, a.tile.h)) a.dem_desc = h->dem_desc;
             else a.tile.w = a.tile.h = 0;
@@ -404,14 +406,16 @@ extern "C" int mppi_combine_partials(MppiHandle* h, const MppiState* state, cons
 }
 
 // ---------------------------------------------------------------- sample-sharded step over peer memory
-static size_t comm_floats(int world, int T) { return (size_t)2 * world * partial_stride(T); }
+static size_t comm_floats(int world, int nblocks, int T) { return (size_t)2 * world * nblocks * partial_stride(T); }
 
 extern "C" int mppi_comm_export(MppiHandle* h, int32_t world, unsigned char* ipc_handle_out)
 {
     if (!h || world < 1 || world > kMaxRanks || !ipc_handle_out) return MPPI_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     if (h->comm_local) return MPPI_ERR_INVALID_ARG;             // already exported
-    const size_t bytes = comm_floats(world, h->T_cap) * sizeof(float) + (size_t)2 * world * sizeof(unsigned);
+    pick_launch(h->p, 1, &h->block, &h->nblocks, &h->pipe);
+    h->comm_nblocks = h->nblocks;
+    const size_t bytes = comm_floats(world, h->comm_nblocks, h->T_cap) * sizeof(float) + (size_t)2 * world * sizeof(unsigned);
     CK(cudaMalloc(&h->comm_local, bytes));
     CK(cudaMemset(h->comm_local, 0, bytes));
     CK(cudaDeviceSynchronize());
@@ -437,7 +441,7 @@ extern "C" int mppi_comm_connect(MppiHandle* h, int32_t rank, int32_t world, con
             h->comm_peer[r] = base;
         }
         h->peers.x[r] = static_cast<float*>(base);
-        h->peers.f[r] = reinterpret_cast<unsigned*>(static_cast<float*>(base) + comm_floats(world, h->T_cap));
+        h->peers.f[r] = reinterpret_cast<unsigned*>(static_cast<float*>(base) + comm_floats(world, h->comm_nblocks, h->T_cap));
     }
     h->peers.rank = rank;
     h->peers.world = world;
@@ -449,7 +453,8 @@ extern "C" int mppi_step_sharded(MppiHandle* h, const MppiState* state, int32_t 
                                  uint64_t seed, uint64_t offset, uint32_t k_begin, void* stream)
 {
     if (!h || !state || h->peers.world < 1) return MPPI_ERR_INVALID_ARG;
-    if (h->p.T != h->T_cap) return MPPI_ERR_UNSUPPORTED;        // the exchange slots are laid out for T_cap
+    pick_launch(h->p, 1, &h->block, &h->nblocks, &h->pipe);
+    if (h->p.T != h->T_cap || h->nblocks != h->comm_nblocks) return MPPI_ERR_UNSUPPORTED;   // slots laid out at export
     return do_step(h, state, nullptr, 1, proj, noise_dev, seed, offset, k_begin, nullptr, (cudaStream_t)stream,
                    false, true);
 }
@@ -458,7 +463,8 @@ extern "C" int mppi_step_sharded_host(MppiHandle* h, const MppiState* state, int
                                       uint64_t offset, uint32_t k_begin, float* cmd_host, void* stream)
 {
     if (!h || !state || !cmd_host || h->peers.world < 1) return MPPI_ERR_INVALID_ARG;
-    if (h->p.T != h->T_cap) return MPPI_ERR_UNSUPPORTED;
+    pick_launch(h->p, 1, &h->block, &h->nblocks, &h->pipe);
+    if (h->p.T != h->T_cap || h->nblocks != h->comm_nblocks) return MPPI_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = do_step(h, state, nullptr, 1, proj, nullptr, seed, offset, k_begin, nullptr, s, true, true);
     if (rc != MPPI_OK) return rc;

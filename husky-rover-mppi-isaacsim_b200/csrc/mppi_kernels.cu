@@ -98,6 +98,12 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// Number of partials the final fold may see: the blocks of this launch, times the ranks in sample-sharded peer mode.
+__host__ __device__ inline int list_cap(const FusedArgs& a)
+{
+    return a.nblocks * ((a.peers.world > 0 && a.rank_partial == nullptr) ? a.peers.world : 1);
+}
+
 // Shared-memory carve-up (floats).  `nblocks` only matters for the block that runs phase 3.
 struct Smem {
     float* nom1;        // [T]
@@ -187,7 +193,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
                                      const Smem& s, float* nominal1, float* nominal2, float* prev1, float* prev2,
                                      float* opt_v, float* opt_w, float* stats, float* rank_partial,
                                      unsigned oob_count, unsigned nan_count, unsigned long long* tr,
-                                     float* host_cmd, unsigned host_seq, const PeerComm* pc = nullptr)
+                                     float* host_cmd, unsigned host_seq)
 {
     const int T = p.T, lane = threadIdx.x & 31, tid = threadIdx.x, B = blockDim.x;
     const int stride = partial_stride(T);
@@ -286,37 +292,6 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
             rank_partial[0] = M; rank_partial[1] = S; rank_partial[2] = __int_as_float(arg); rank_partial[3] = S2;
         }
         for (int col = lane; col < 2 * T; col += 32) rank_partial[kPartialHeader + col] = s.acc[col];
-        return;
-    }
-
-    if (pc != nullptr && pc->world > 0) {
-        // ---- sample-sharded mode with peer memory: exchange the rank partials inside this launch
-        const int world = pc->world, me = pc->rank;
-        const unsigned seq = pc->seq;
-        const size_t slot = ((size_t)(seq & 1u) * world + me) * stride;
-        for (int r = 0; r < world; ++r) {                  // NVLink stores (plain local stores for r == me)
-            float* dst = pc->x[r] + slot;
-            if (lane == 0) { dst[0] = M; dst[1] = S; dst[2] = __int_as_float(arg); dst[3] = S2; }
-            for (int col = lane; col < 2 * T; col += 32) dst[kPartialHeader + col] = s.acc[col];
-        }
-        // __syncwarp orders every lane's stores before the system-scope release of the flags below
-        __syncwarp();
-        if (lane < world) {
-            unsigned int* theirs = pc->f[lane] + (seq & 1u) * world + me;
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
-            const unsigned int* mine = pc->f[me] + (seq & 1u) * world + lane;
-            unsigned got;
-            for (unsigned spin = 0;; ++spin) {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
-                if (got == seq) break;
-                __nanosleep(64);
-                if (spin > (1u << 24)) __trap();           // a missing rank must fail loudly, never hang the GPU
-            }
-        }
-        __syncwarp();
-        combine_and_finalize(p, st, pc->x[me] + (size_t)(seq & 1u) * world * stride, world, s, nominal1, nominal2,
-                             prev1, prev2, opt_v, opt_w, stats, nullptr, oob_count, nan_count, nullptr, host_cmd,
-                             host_seq, nullptr);
         return;
     }
 
@@ -493,7 +468,16 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
     if (tid == 0) trace_stamp(A, 10);
 
     const int stride = partial_stride(T);
-    float* part = A.partials + ((size_t)rover * A.nblocks + blockIdx.x) * stride;
+    // Where this block's partial goes: the handle's partial array, or -- sample-sharded step with peer memory --
+    // slot (this rank, this block) of EVERY rank's exchange buffer (NVLink stores; the local copy is one of them).
+    const bool flat = (rover == 0) && (A.peers.world > 0) && (A.rank_partial == nullptr);
+    const int ndst = flat ? A.peers.world : 1;
+    const size_t xoff = flat ? (((size_t)(A.peers.seq & 1u) * A.peers.world + A.peers.rank) * A.nblocks + blockIdx.x) * stride : 0;
+    float* part_local = A.partials + ((size_t)rover * A.nblocks + blockIdx.x) * stride;
+    auto put = [&](int idx, float v) {
+        if (!flat) { part_local[idx] = v; return; }
+        for (int r = 0; r < ndst; ++r) A.peers.x[r][xoff + idx] = v;
+    };
     {
         const int P = (T + 1) >> 1;                       // step pairs
         const int G = (B >= 2 * P && n_e > 1) ? B / P : 1;   // entry groups working in parallel
@@ -544,14 +528,14 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
             const int prw = (G > 1) ? tid : pr;
             if (writer) {
                 const int t = 2 * prw;
-                part[kPartialHeader + t] = a1a;
-                part[kPartialHeader + T + t] = a2a;
-                if (t + 1 < T) { part[kPartialHeader + t + 1] = a1b; part[kPartialHeader + T + t + 1] = a2b; }
+                put(kPartialHeader + t, a1a);
+                put(kPartialHeader + T + t, a2a);
+                if (t + 1 < T) { put(kPartialHeader + t + 1, a1b); put(kPartialHeader + T + t + 1, a2b); }
             }
             if (G > 1) break;
         }
     }
-    if (tid == 0) { part[0] = m_b; part[1] = s_b; part[2] = __int_as_float(arg_b); part[3] = s2_b; trace_stamp(A, 5); }
+    if (tid == 0) { put(0, m_b); put(1, s_b); put(2, __int_as_float(arg_b)); put(3, s2_b); trace_stamp(A, 5); }
 
     // ---------------- phase 3: last block folds everything
     // publish: the barrier orders every thread's partial stores before thread 0's gpu-scope release
@@ -562,9 +546,13 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
         // release only: the partials of this block are ordered before the ticket.  The last block reads the other
         // blocks' partials with ld.global STRONG.GPU loads issued after (and control-dependent on) the ticket value,
         // straight from L2 where every released partial already is -- an acquire here would only add an L1
-        // invalidation (CCTL.IVALL) to the tail of every block.
-        asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;"
-                     : "=r"(ticket) : "l"(&A.counters[rover * kCounterStride + 0]) : "memory");
+        // invalidation (CCTL.IVALL) to the tail of every block.  With peer stores in flight the release is system-wide.
+        if (flat)
+            asm volatile("atom.release.sys.global.add.u32 %0, [%1], 1;"
+                         : "=r"(ticket) : "l"(&A.counters[rover * kCounterStride + 0]) : "memory");
+        else
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;"
+                         : "=r"(ticket) : "l"(&A.counters[rover * kCounterStride + 0]) : "memory");
         s.red_i[63] = (ticket == (unsigned)(A.nblocks - 1));
         trace_stamp(A, 11);
     }
@@ -575,13 +563,36 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
     if (A.trace != nullptr && rover == 0 && tid == 0) A.trace[(size_t)blockIdx.x * kTraceSlots + 23] = (unsigned long long)clock64();
     const unsigned oob_count = __ldcg(&A.counters[rover * kCounterStride + 1]);
     const unsigned nan_count = __ldcg(&A.counters[rover * kCounterStride + 2]);
-    combine_and_finalize(p, st, A.partials + (size_t)rover * A.nblocks * stride, A.nblocks, s,
+    const float* all_parts = A.partials + (size_t)rover * A.nblocks * stride;
+    int n_parts = A.nblocks;
+    if (flat) {
+        // every block of this rank has released its partial into every peer: tell the peers, wait for theirs.  The
+        // partials of all ranks then sit in rank order, block order = global sample order, in this rank's buffer.
+        const int world = A.peers.world, me = A.peers.rank;
+        const unsigned seq = A.peers.seq;
+        if (tid < world) {
+            unsigned int* theirs = A.peers.f[tid] + (seq & 1u) * world + me;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
+            const unsigned int* mine = A.peers.f[me] + (seq & 1u) * world + tid;
+            unsigned got;
+            for (unsigned spin = 0;; ++spin) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+                if (got == seq) break;
+                __nanosleep(64);
+                if (spin > (1u << 24)) __trap();           // a missing rank must fail loudly, never hang the GPU
+            }
+        }
+        __syncthreads();
+        all_parts = A.peers.x[me] + (size_t)(seq & 1u) * world * A.nblocks * stride;
+        n_parts = world * A.nblocks;
+    }
+    combine_and_finalize(p, st, all_parts, n_parts, s,
                          nominal1, nominal2, A.prev1 + (size_t)rover * T, A.prev2 + (size_t)rover * T,
                          A.opt_v + (size_t)rover * T, A.opt_w + (size_t)rover * T,
                          A.stats + (size_t)rover * kStatsStride,
                          A.rank_partial ? A.rank_partial + (size_t)rover * stride : nullptr, oob_count, nan_count,
                          (A.trace != nullptr && rover == 0) ? A.trace + (size_t)blockIdx.x * kTraceSlots : nullptr,
-                         (rover == 0) ? A.host_cmd : nullptr, A.host_seq, (rover == 0) ? &A.peers : nullptr);
+                         (rover == 0) ? A.host_cmd : nullptr, A.host_seq);
     if (tid == 0 && A.loop.state != nullptr && A.rank_partial == nullptr)
         loop_advance(A, st, A.stats + (size_t)rover * kStatsStride);
     if (tid == 0) {                                       // re-arm for the next launch
@@ -636,7 +647,7 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
     const MppiParams& p = A.p;
     const int T = p.T, K = p.K, B = blockDim.x, tid = threadIdx.x;
     const int rover = blockIdx.y;
-    const Smem s = carve(smem_raw, T, B, A.nblocks);
+    const Smem s = carve(smem_raw, T, B, list_cap(A));
     if (tid == 0) {
         trace_stamp(A, 0);
         if (A.trace != nullptr && rover == 0) {
@@ -804,8 +815,8 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     int role = tid >> 5;
     if (((blockIdx.x / 148) & 1) && (role == 2 || role == 3)) role ^= 1;
     const int rover = blockIdx.y;
-    const Smem s = carve(smem_raw, T, kPipeThreads, A.nblocks);
-    PipeSmem& ps = *reinterpret_cast<PipeSmem*>(smem_raw + pipe_smem_offset_floats(T, A.nblocks));
+    const Smem s = carve(smem_raw, T, kPipeThreads, list_cap(A));
+    PipeSmem& ps = *reinterpret_cast<PipeSmem*>(smem_raw + pipe_smem_offset_floats(T, list_cap(A)));
     float* tile = reinterpret_cast<float*>(reinterpret_cast<char*>(&ps) + ((sizeof(PipeSmem) + 127) & ~(size_t)127));
     if (tid == 0) {
         trace_stamp(A, 0);
@@ -1254,7 +1265,7 @@ static cudaError_t ensure_smem(Kern k, size_t bytes)
 cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, cudaStream_t s)
 {
     const dim3 grid(a.nblocks, n_rovers);
-    const size_t smem = fused_smem_bytes(a.p.T, block, a.nblocks);
+    const size_t smem = fused_smem_bytes(a.p.T, block, list_cap(a));
     cudaError_t e;
 #define MPPI_LAUNCH_FUSED(PROJ, INJ)                                              \
     do {                                                                          \
@@ -1279,7 +1290,7 @@ size_t pipe_smem_bytes_no_tile(int T, int nblocks)
 cudaError_t launch_fused_pipe(const FusedArgs& a, int proj, int n_rovers, cudaStream_t s)
 {
     const dim3 grid(a.nblocks, n_rovers);
-    const size_t smem = pipe_smem_bytes_no_tile(a.p.T, a.nblocks) + (size_t)a.tile.w * a.tile.h * sizeof(float);
+    const size_t smem = pipe_smem_bytes_no_tile(a.p.T, list_cap(a)) + (size_t)a.tile.w * a.tile.h * sizeof(float);
     cudaError_t e;
 #define MPPI_LAUNCH_PIPE(PROJ, INJ)                                                    \
     do {                                                                               \

@@ -18,10 +18,12 @@ constexpr int kStatsStride = 8;       // floats per rover in the stats buffer
 constexpr int kCounterStride = 4;     // uints per rover: {ticket, oob, nan, 0}
 
 // Peer exchange of the sample-sharded multi-GPU step (one process per GPU; buffers mapped with CUDA IPC).
-// Rank r owns x[r]: [2 parities][world][partial_stride(T)] floats and f[r]: [2][world] arrival flags.  The last block
-// of rank g's fused kernel stores its rank partial into slot g of EVERY rank's buffer over NVLink, releases one flag
-// per peer, waits for the world's flags in its own buffer and folds the partials in rank order: compute + exchange +
-// update in ONE launch, no collective library call and no second kernel.
+// Rank r owns x[r]: [2 parities][world][nblocks][partial_stride(T)] floats and f[r]: [2][world] arrival flags.  EVERY
+// block of rank g's fused kernel stores its softmax partial into slot (g, block) of every rank's buffer over NVLink as
+// soon as it has it; the rank's last block then releases one flag per peer, waits for the world's flags in its own
+// buffer and folds all world x nblocks partials in global block (= global sample) order, exactly as an unsharded run
+// over the same blocks would: compute + exchange + update in ONE launch, no collective library call, no second kernel,
+// one combine.
 constexpr int kMaxRanks = 8;
 struct PeerComm {
     float* x[kMaxRanks];

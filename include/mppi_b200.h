@@ -184,9 +184,10 @@ int mppi_partial_floats(int32_t T);   /* 4 + 2T */
  *   1. every rank: mppi_comm_export(h, world, handle)        -> 64-byte CUDA IPC handle of its exchange buffer
  *   2. the ranks all-gather the handles (any host transport; sharding.py uses torch.distributed)
  *   3. every rank: mppi_comm_connect(h, rank, world, handles)   with handles = world x 64 bytes, in rank order
- *   4. per iteration, on every rank: mppi_step_sharded(...)  -- the last block of the launch stores the rank
- *      partial into every peer, releases a flag per peer, waits (bounded; traps on a missing rank) for the world's
- *      flags and folds the partials in rank order, so all ranks finish with the identical nominal and command.
+ *   4. per iteration, on every rank: mppi_step_sharded(...)  -- every block of the launch stores its softmax partial
+ *      into every rank's buffer; the rank's last block releases a flag per peer, waits (bounded; traps on a missing
+ *      rank) for the world's flags and folds all world x nblocks partials in global block order, so all ranks finish
+ *      with the identical nominal and command -- bitwise what one GPU would compute over the same blocks.
  * All ranks must call mppi_step_sharded the same number of times. */
 int mppi_comm_export(MppiHandle *h, int32_t world, unsigned char *ipc_handle_out /* [64] */);
 int mppi_comm_connect(MppiHandle *h, int32_t rank, int32_t world, const unsigned char *ipc_handles);

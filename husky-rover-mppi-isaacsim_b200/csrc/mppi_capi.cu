@@ -316,7 +316,7 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     if (h->pipe && !states_dev && n_rovers == 1 && proj == MPPI_PROJ_3D && h->nblocks <= 148)
     {
         a.tile = plan_dem_tile(h->p, h->terrain,
-                               strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks * (a.peers.world > 0 ? a.peers.world : 1)));
+                               strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks * (a.peers.world > 0 && h->nblocks <= 148 ? a.peers.world : 1)));
         if (a.tile.w > 0) {
             if (encode_dem_desc(h, h->terrain, a.tile.w, a.tile.h)) a.dem_desc = h->dem_desc;
             else a.tile.w = a.tile.h = 0;
@@ -445,6 +445,7 @@ extern "C" int mppi_comm_connect(MppiHandle* h, int32_t rank, int32_t world, con
     }
     h->peers.rank = rank;
     h->peers.world = world;
+    h->peers.nblocks = h->comm_nblocks;
     h->peers.seq = 0;
     return MPPI_OK;
 }

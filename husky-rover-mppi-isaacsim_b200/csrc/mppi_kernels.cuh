@@ -29,6 +29,7 @@ struct PeerComm {
     float* x[kMaxRanks];
     unsigned int* f[kMaxRanks];
     int32_t rank, world;              // world == 0: no peer exchange
+    int32_t nblocks;                  // blocks per rank the buffers were laid out for
     uint32_t seq;                     // step sequence number (parity = seq & 1 selects the buffer half)
 };
 

@@ -25,13 +25,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    K_total, T = 4096, 60
     dem, cm, hw = terrain("C1")
     dem_t, cm_t = torch.from_numpy(dem).to(dev), torch.from_numpy(cm).to(dev)
     st = make_state(-60.57, -60.23, goal_x=65.8, goal_y=65.4)
-    nom = np.full(T, 0.35, np.float32)
     results = {}
-    for lam in (0.3, 2000.0):
+    # (K_total, T): the latency regime (flat exchange: every block's partial goes to every rank, bitwise the unsharded
+    # result) and the throughput regime (thousands of blocks: two-level exchange of one rank partial)
+    for K_total, T, lam in ((4096, 60, 0.3), (4096, 60, 2000.0), (32768 * world, 20, 2000.0)):
+        nom = np.full(T, 0.35, np.float32)
+        flat = (K_total // world) <= 148 * 32
         # reference: the whole problem on this GPU
         full = Core(K_total, T, device=local, lambda_=lam)
         full.set_terrain(dem_t, hw, cm_t)
@@ -54,10 +56,10 @@ def main():
                 assert got[1]["min_cost"] == ref[1]["min_cost"]
                 err = float(np.max(np.abs(got[0] - ref[0]) / np.maximum(np.abs(ref[0]), 1e-3)))
                 assert err < 1e-5, (transport, lam, it, err)
-                if transport == "p2p":
+                if transport == "p2p" and flat:
                     # every block's partial is folded in global block order, exactly as the unsharded launch does
                     assert np.array_equal(got[0], ref[0]), (lam, it)
-            results[(transport, lam)] = got[0]
+            results[transport] = got[0]
             # every rank must hold the identical nominal (bitwise): gather and compare
             mine = torch.from_numpy(got[0]).to(dev)
             every = torch.empty((world, T), device=dev)
@@ -65,7 +67,7 @@ def main():
             assert bool((every == every[0]).all()), (transport, lam)
             core.close()
         # the NCCL transport folds per rank first, then across ranks: same value up to the summation order
-        assert np.allclose(results[("p2p", lam)], results[("nccl", lam)], rtol=1e-5, atol=1e-7)
+        assert np.allclose(results["p2p"], results["nccl"], rtol=1e-5, atol=1e-7)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK_OK world", world)

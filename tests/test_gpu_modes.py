@@ -296,3 +296,31 @@ def test_visualiser_export_and_block_change(oracle):
     torch.cuda.synchronize()
     assert ctrl.stats()["nan"] == 0
     ctrl.close()
+
+
+def test_shared_memory_dem_tile_changes_no_bit(oracle, monkeypatch):
+    """The pipelined kernel stages the reachable DEM window in shared memory with a TMA tensor copy when it fits.
+    With the tile switched off (MPPI_NO_DEM_TILE) the same step reads the DEM through L1 / L2: identical bits."""
+    import torch
+    K, T = 2048, 60
+    st = state_struct(default_state())
+    outs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("MPPI_NO_DEM_TILE", "1")
+        else:
+            monkeypatch.delenv("MPPI_NO_DEM_TILE", raising=False)
+        core, *_ = make_core(K, T, lambda_=30.0, variant=2)
+        core.step(st, seed=8, offset=4)
+        torch.cuda.synchronize()
+        outs.append((core.costs[0].cpu().numpy().copy(), core.optimal_u1[0].cpu().numpy().copy(), core.read_stats()))
+        core.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2]["argmin"] == outs[1][2]["argmin"] and outs[0][2]["oob"] == 0
+    # and both equal the oracle
+    dem, cm, hw = terrain("C1")
+    eps = oracle.philox_normals(8, 4, K, T)
+    z = np.zeros(T, np.float32)
+    ref = oracle.mppi_step(oracle.make_params(K=K, T=T, lam=30.0), dem, hw, cm, default_state(), z, z, eps[0], eps[1],
+                           dump=["cost"])
+    assert np.array_equal(outs[0][0], ref.dump["cost"])

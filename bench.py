@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the closed-loop (run()) measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--rovers", type=int, default=512, help="C4 only: rovers per GPU (4096 rovers / 8 GPUs)")
+    ap.add_argument("--critics", choices=["auto", "reference", "ext"], default="auto",
+                    help="reference: the four active critics of the reference; ext: + body-slope (critics_warp.py:131-166), "
+                         "roll and pitch critics (MppiParams.cw_slope_path / cw_roll / cw_pitch); auto: ext for C5, the "
+                         "configuration BASELINE.json names with roll/pitch/slope critics, reference otherwise")
     ap.add_argument("--K", type=int, default=0, help="override the workload's samples per GPU (diagnostics)")
     ap.add_argument("--T", type=int, default=0, help="override the workload's horizon (diagnostics)")
     return ap.parse_args()
@@ -82,15 +86,24 @@ def build_workload(name, K_override=0, T_override=0):
     return w, dem, cm, start, goal
 
 
+EXT_CRITICS = dict(cw_slope_path=50.5, cw_roll=400.0, cw_pitch=250.0)
+
+
+def critic_weights(args):
+    """Optional critic weights of this run (see --critics)."""
+    ext = args.critics == "ext" or (args.critics == "auto" and args.workload == "C5")
+    return dict(EXT_CRITICS) if ext else {}
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(w, dem, cm, start, goal, seconds, steps=None, warmup=0, K=None):
+def cpu_reference_run(w, dem, cm, start, goal, seconds, steps=None, warmup=0, K=None, critics=None):
     """Times the C port of the reference path (oracle/mppi_oracle.c, libm math) on all host cores."""
     from oracle import oracle_c as oc
     oc.build()
     K = K or w.K
     T = w.T
     threads = oc.num_threads()
-    p = oc.make_params(K=K, T=T, math=oc.MATH_LIBM)
+    p = oc.make_params(K=K, T=T, math=oc.MATH_LIBM, **(critics or {}))
     st = dict(x=start[0], y=start[1], hx=1.0, hy=0.0, hz=0.0, wheel_l=0.0, wheel_r=0.0, sigma1=0.25, sigma2=0.25,
               goal_x=goal[0], goal_y=goal[1], goal_theta=2.2)
     rng = np.random.default_rng(0)
@@ -119,13 +132,15 @@ def run_reference_arm(args):
     if rank != 0:
         return
     w, dem, cm, start, goal = build_workload(args.workload, args.K, args.T)
-    base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=max(5, args.warmup))
+    base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=max(5, args.warmup),
+                                    critics=critic_weights(args))
     line = {
         "impl": "reference", "metric": "MPPI sample-steps/s", "value": base["value"], "unit": "sample-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w.name, "K": w.K, "T": w.T, "dem": f"{w.grid_size}x{w.grid_size} f32",
                    "costmap": f"{w.costmap_size}x{w.costmap_size} f32",
+                   "critics": "reference 4 + body-slope, roll, pitch" if critic_weights(args) else "reference 4",
                    "note": "the reference's GPU path needs NVIDIA Warp (absent, no network); this arm is the C port "
                            "of its kernels on the host cores"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -348,7 +363,8 @@ def main():
     K, T = w.K, w.T                       # per-GPU samples
     K_total = K * n_gpus
     core = Core(K, T, device=local_rank, math=args.math,
-                variant={"auto": capi.VARIANT_AUTO, "mono": capi.VARIANT_MONO, "pipe": capi.VARIANT_PIPE}[args.variant])
+                variant={"auto": capi.VARIANT_AUTO, "mono": capi.VARIANT_MONO, "pipe": capi.VARIANT_PIPE}[args.variant],
+                **critic_weights(args))
     dem = torch.from_numpy(dem_np).to(dev)
     cm = torch.from_numpy(cm_np).to(dev)
     core.set_terrain(dem, w.half_width, cm)
@@ -506,6 +522,8 @@ def main():
             "config": {"workload": w.name, "K_per_gpu": K, "K_total": K_total, "T": T,
                        "dem": f"{w.grid_size}x{w.grid_size} f32", "costmap": f"{w.costmap_size}x{w.costmap_size} f32",
                        "math": args.math, "variant": args.variant, "noise": "in-kernel Philox4x32-10 + Box-Muller", "proj": "3d",
+                       "critics": ("reference 4 (path, wheel slope, speed, obstacle) + body-slope, roll, pitch"
+                                   if critic_weights(args) else "reference 4 (path, wheel slope, speed, obstacle)"),
                        "l2": "flushed between timed iterations (256 MiB fill)" if do_flush else "warm",
                        "parallelism": "single GPU" if n_gpus == 1 else
                        (f"sample-sharded x{n_gpus}, {core.partial_floats() * 4} B softmax partial per rank exchanged "
@@ -526,7 +544,8 @@ def main():
             "stats": core.read_stats(),
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
-            base, _ = cpu_reference_run(w, dem_np, cm_np, start, goal, seconds=args.cpu_seconds)
+            base, _ = cpu_reference_run(w, dem_np, cm_np, start, goal, seconds=args.cpu_seconds,
+                                        critics=critic_weights(args))
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
     if world > 1:

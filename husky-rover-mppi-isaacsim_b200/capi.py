@@ -38,6 +38,10 @@ class MppiParams(C.Structure):
         ("near_goal_cut", C.c_float), ("speed_eps", C.c_float), ("pf_eps", C.c_float),
         ("pf_near_gain", C.c_float), ("slope_eps", C.c_float), ("slope_gain", C.c_float),
         ("horizon", C.c_float), ("target_speed", C.c_float), ("input_model", C.c_int32),
+        # optional critics (weight 0 = off): dormant reference critics, then the roll / pitch / effort extensions
+        ("cw_orient", C.c_float), ("cw_slope_path", C.c_float), ("cw_goal_angle", C.c_float),
+        ("goal_angle_radius", C.c_float), ("cw_roll", C.c_float), ("cw_pitch", C.c_float), ("cw_effort", C.c_float),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -62,7 +66,7 @@ class MppiOutputs(C.Structure):
 class MppiDebugDump(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("u1", "u2", "v", "w", "traj", "heading", "lw", "rw",
-                 "dem_ij", "lw_ij", "rw_ij", "cm_ij", "critics", "weights")]
+                 "dem_ij", "lw_ij", "rw_ij", "cm_ij", "critics", "weights", "critics_ext")]
 
 
 # every symbol include/mppi_b200.h declares: (name, restype, argtypes)
@@ -125,7 +129,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
         return LIB_PATH
-    r = subprocess.run(["make", "-C", CSRC] + (["-B"] if force else []), capture_output=True, text=True)
+    r = subprocess.run(["make", "-j4", "-C", CSRC] + (["-B"] if force else []), capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode != 0:
@@ -148,7 +152,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.mppi_abi_version() != 2:
+        if L.mppi_abi_version() != 3:
             raise MppiError("libmppi_b200.so ABI version mismatch")
         _lib = L
     return _lib

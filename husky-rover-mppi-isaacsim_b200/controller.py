@@ -105,10 +105,15 @@ class MPPI_Controller:
       math    "strict" (bit-reproducible vs the oracle) | "fast"
       device  CUDA device index
       seed    Philox seed (the reference seeds its host generator with 42, MPPI_isaac.py:409)
+      critic_weights  dict of critic weights (MppiParams.cw_*), e.g. {"cw_orient": 1.0, "cw_slope_path": 50.5} to
+              re-enable the critics the reference keeps commented out (critics_warp.py:324,326), "cw_goal_angle"
+              (critics_warp.py:5-41) or the roll / pitch / effort extensions.  Empty = the reference's four critics
+              with its weights.
     """
 
     def __init__(self, surface, robot, config_path, goal_x, goal_y, goal_orientation, *, math: str = "strict",
-                 device: int = 0, seed: int = 42, overrides: Optional[dict] = None):
+                 device: int = 0, seed: int = 42, overrides: Optional[dict] = None,
+                 critic_weights: Optional[dict] = None):
         with open(config_path, "r") as f:
             config = yaml.safe_load(f)
         self.rng = np.random.default_rng(seed=42)
@@ -139,6 +144,10 @@ class MPPI_Controller:
         self.horizon = self.dt * self.v_max_linear * self.number_of_iterations     # MPPI_isaac.py:440
 
         self.math = {"strict": capi.MATH_STRICT, "fast": capi.MATH_FAST}[math]
+        self.critic_weights = dict(critic_weights or {})
+        for k in self.critic_weights:
+            if not (k.startswith("cw_") or k == "goal_angle_radius") or not hasattr(capi.MppiParams, k):
+                raise ValueError(f"unknown critic weight {k!r}")
         self.device = torch.device("cuda", device)
         self.seed = int(seed)
         self._handle = None
@@ -161,6 +170,8 @@ class MPPI_Controller:
         p.r_wheels = float(self.robot.radius)
         p.horizon = self.horizon
         p.target_speed = self.v_max_linear
+        for k, val in self.critic_weights.items():
+            setattr(p, k, float(val))
         return p
 
     def warp_setup(self):
@@ -318,7 +329,7 @@ class MPPI_Controller:
         dev = self.device
         shapes = {"u1": (K, T), "u2": (K, T), "v": (K, T), "w": (K, T), "traj": (K, T, 3), "heading": (K, T, 3),
                   "lw": (K, T, 3), "rw": (K, T, 3), "dem_ij": (K, T, 2), "lw_ij": (K, T, 2), "rw_ij": (K, T, 2),
-                  "cm_ij": (K, T, 2), "critics": (K, 4), "weights": (K,)}
+                  "cm_ij": (K, T, 2), "critics": (K, 4), "weights": (K,), "critics_ext": (K, 6)}
         d = capi.MppiDebugDump()
         out = {}
         for name in which:

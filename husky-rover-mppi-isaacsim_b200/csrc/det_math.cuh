@@ -104,5 +104,20 @@ __device__ __forceinline__ float expf_det(float x)
     return (res * s1) * s2;
 }
 
+// atan(x), any x: atan(+-inf) = +-pi/2, atan(NaN) = NaN (goal-angle critic, critics_warp.py:37).  Evaluated once per
+// sample at most, so the two IEEE divisions are spelled __fdiv_rn whatever the flavour's division is.
+__device__ __forceinline__ float atanf_det(float xx)
+{
+    float x = fabsf(xx), y = 0.0f;
+    if (x > 0x1.3504f4p+1f) { y = 0x1.921fb6p+0f; x = -__fdiv_rn(1.0f, x); }
+    else if (x > 0x1.a8279ap-2f) { y = 0x1.921fb6p-1f; x = __fdiv_rn(x - 1.0f, x + 1.0f); }
+    const float z = x * x;
+    float p = fmaf(0x1.49e1a2p-4f, z, -0x1.1c370ap-3f);
+    p = fmaf(p, z, 0x1.9924bep-3f);
+    p = fmaf(p, z, -0x1.555454p-2f);
+    const float r = y + fmaf(p * z, x, x);
+    return copysignf(r, xx);
+}
+
 }  // namespace dm
 }  // namespace mppi

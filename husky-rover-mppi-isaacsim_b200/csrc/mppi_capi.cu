@@ -95,6 +95,7 @@ extern "C" int mppi_default_params(MppiParams* p, int32_t K, int32_t T)
     p->slope_eps = 1e-6f; p->slope_gain = 5.0f;
     p->horizon = (float)(0.045 * 2.0 * (double)T);
     p->target_speed = 2.0f;
+    p->goal_angle_radius = 0.5f;                 // critics_warp.py:33; the optional critics' weights stay 0 (off)
     return MPPI_OK;
 }
 
@@ -116,6 +117,17 @@ static void pick_launch(const MppiParams& p, int n_rovers, int* block, int* nblo
     *block = b;
     *nblocks = (K + b - 1) / b;
 }
+
+// Kernel namespace of a parameter set: arithmetic flavour x (optional critics compiled in or not).  The XC builds are
+// used only when one of the optional critic weights is non-zero, so the default hot path is untouched by them.
+static bool wants_xc(const MppiParams& p)
+{
+    return p.cw_orient != 0.f || p.cw_slope_path != 0.f || p.cw_goal_angle != 0.f || p.cw_roll != 0.f ||
+           p.cw_pitch != 0.f || p.cw_effort != 0.f;
+}
+#define MPPI_BY_NS(P, CALL)                                                                             \
+    (wants_xc(P) ? (((P).math == MPPI_MATH_FAST) ? fast_xc::CALL : strict_xc::CALL)                       \
+                 : (((P).math == MPPI_MATH_FAST) ? fast::CALL : strict::CALL))
 
 static bool params_ok(const MppiParams* p)
 {
@@ -316,7 +328,7 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     if (h->pipe && !states_dev && n_rovers == 1 && proj == MPPI_PROJ_3D && h->nblocks <= 148)
     {
         a.tile = plan_dem_tile(h->p, h->terrain,
-                               strict::pipe_smem_bytes_no_tile(h->p.T, h->nblocks * (a.peers.world > 0 && h->nblocks <= 148 ? a.peers.world : 1)));
+                               MPPI_BY_NS(h->p, pipe_smem_bytes_no_tile(h->p.T, h->nblocks * (a.peers.world > 0 && h->nblocks <= 148 ? a.peers.world : 1))));
         if (a.tile.w > 0) {
             if (encode_dem_desc(h, h->terrain, a.tile.w, a.tile.h)) a.dem_desc = h->dem_desc;
             else a.tile.w = a.tile.h = 0;
@@ -325,11 +337,9 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     if (h->timing) CK(cudaEventRecord(h->ev0, s));
     cudaError_t e;
     if (h->pipe)
-        e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_fused_pipe(a, proj, n_rovers, s)
-                                          : strict::launch_fused_pipe(a, proj, n_rovers, s);
+        e = MPPI_BY_NS(h->p, launch_fused_pipe(a, proj, n_rovers, s));
     else
-        e = (h->p.math == MPPI_MATH_FAST) ? fast::launch_fused(a, proj, n_rovers, h->block, s)
-                                          : strict::launch_fused(a, proj, n_rovers, h->block, s);
+        e = MPPI_BY_NS(h->p, launch_fused(a, proj, n_rovers, h->block, s));
     if (e != cudaSuccess) return cuda_fail(e, "launch_fused");
     if (h->timing) { CK(cudaEventRecord(h->ev1, s)); h->timed_valid = true; }
     return MPPI_OK;
@@ -675,7 +685,7 @@ extern "C" int mppi_build_costmap(int32_t device, const double* obstacles_host, 
 
 extern "C" int mppi_test_detmath(int32_t fn, const float* x, float* y0, float* y1, int32_t n, void* stream)
 {
-    if (!x || !y0 || n < 1 || fn < 0 || fn > 3) return MPPI_ERR_INVALID_ARG;
+    if (!x || !y0 || n < 1 || fn < 0 || fn > 4) return MPPI_ERR_INVALID_ARG;
     cudaError_t e = strict::launch_detmath(fn, x, y0, y1, n, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch_detmath");
     return MPPI_OK;

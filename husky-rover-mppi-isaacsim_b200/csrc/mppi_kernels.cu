@@ -682,6 +682,8 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
 
 #ifndef MPPI_MONO_MINBLOCKS
 #define MPPI_MONO_MINBLOCKS 2       // A/B knob: resident 256-thread blocks per SM the register allocation must allow
+                                    // (the -DMPPI_XC build fits the same 128 registers without spilling; left alone it
+                                    // takes 156 and C5 no longer fits one wave: 402 us instead of 300)
 #endif
 template <int PROJ, bool INJECT>
 __global__ void __launch_bounds__(kMaxBlock, MPPI_MONO_MINBLOCKS)
@@ -731,7 +733,7 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
             rollout_sample<PROJ, INJECT, false>(p, st, ter, sc, nk, s, a, kg, eps1, eps2);
         else
             rollout_sample<PROJ, INJECT, true>(p, st, ter, sc, nk, s, a, kg, eps1, eps2);
-        cost = sample_cost(p, sc, a, nullptr);
+        cost = sample_cost(p, st, sc, a, nullptr);
         A.costs[(size_t)rover * K + k_local] = cost;
         my_oob = (unsigned)(a.oob + unit_violation(a.dev));
         if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }   // a NaN rollout gets zero weight
@@ -771,7 +773,8 @@ struct PipeSmem {
     float ring_u[kPipeStages][kPipeChunk][2][32];     // u1, u2
     float ring_a[kPipeStages][kPipeChunk][3][32];     // v, sin(w dt), cos(w dt)
     float ring_b[kPipeStages][kPipeChunk][8][32];     // x, y, n.xyz, cur.xyz
-    float crit[6][32];                                // speed, slope, obs, pf_near, last_x, last_y
+    float crit[kXC ? 12 : 6][32];                     // speed, slope, obs, pf_near, last_x, last_y
+                                                      // (+ effort, roll, pitch, slope_c, pen_x, pen_y with the optional critics)
     int oob[6][32];
     unsigned long long tile_bar;                      // completes when the TMA copies of the DEM tile have landed
 };
@@ -954,7 +957,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         }
     } else if (role == ROLE_FILTER) {
         // ---- wheel filter u -> (v, w) (sequential in t) + speed critic
-        float wl = st.wheel_l, wr = st.wheel_r, speed = 0.0f;
+        float wl = st.wheel_l, wr = st.wheel_r, speed = 0.0f, effort = 0.0f;
         for (int c = 0; c < nchunks; ++c) {
             const int sg = c % kPipeStages;
             const unsigned ph = (c / kPipeStages) & 1;
@@ -965,7 +968,9 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                 const int t = c * kPipeChunk + i;
                 if (t < T) {
                     float v, sn, cs;
-                    role_filter(p, sc, wl, wr, ps.ring_u[sg][i][0][lane], ps.ring_u[sg][i][1][lane], v, sn, cs, speed);
+                    const float u1 = ps.ring_u[sg][i][0][lane], u2 = ps.ring_u[sg][i][1][lane];
+                    role_filter(p, sc, wl, wr, u1, u2, v, sn, cs, speed);
+                    if (kXC) effort += u1 * u1 + u2 * u2;
                     ps.ring_a[sg][i][0][lane] = v; ps.ring_a[sg][i][1][lane] = sn; ps.ring_a[sg][i][2][lane] = cs;
                 }
             }
@@ -973,6 +978,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             mbar_arrive(&ps.full_a[sg]);
         }
         ps.crit[0][lane] = speed;
+        if (kXC) ps.crit[6][lane] = effort;
     } else if (role == ROLE_CHAIN) {
         // ---- chain: the recurrence
         float x = st.x, y = st.y;
@@ -1022,8 +1028,8 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         if (lane == 0) trace_stamp(A, 3);
     } else if (role == ROLE_WHEELS) {
         // ---- wheels + slope critic
-        float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e;
-        float slope = 0.0f;
+        float3 lw_e = make_float3(0.f, 0.f, 0.f), rw_e = lw_e, ctr_e = lw_e;
+        float slope = 0.0f, roll = 0.0f, pitch = 0.0f, slope_c = 0.0f;
         const bool use_tile = (tg.w > 0) && (PROJ == MPPI_PROJ_3D) && (nfast > 0);
         if (use_tile) mbar_wait(&ps.tile_bar, 0);
         auto chunk = [&](int c, auto fast_tag, auto tile_tag) {
@@ -1039,6 +1045,15 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                     role_wheels<PROJ, !FAST, TILE>(p, ter, t, o[0], o[32], make_float3(o[64], o[96], o[128]),
                                                    make_float3(o[160], o[192], o[224]), lw_e, rw_e, slope, oob,
                                                    tile, tg.w, tg.i0, tg.j0);
+                    if (kXC) {
+                        // optional critics of the even steps: lw_e / rw_e now hold this step's wheel points; the
+                        // body height is re-interpolated here (the chain role does not need it)
+                        int bi, bj, dummy = 0;
+                        const Quad q = TILE ? corners_tile(ter, tile, tg, o[0], o[32])
+                                            : corners<!FAST>(ter, o[0], o[32], bi, bj, dummy);
+                        extras_even(p, t, o[0], o[32], bilinear(o[0], o[32], q, ter.rres), lw_e.z, rw_e.z, o[224],
+                                    roll, pitch, slope_c, ctr_e);
+                    }
                 }
             }
             mbar_arrive(&ps.empty_b[sg]);
@@ -1048,11 +1063,12 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         else { for (; c < nfast; ++c) chunk(c, FastTag<true>{}, FastTag<false>{}); }
         for (; c < nchunks; ++c) chunk(c, FastTag<false>{}, FastTag<false>{});
         ps.crit[1][lane] = slope;
+        if (kXC) { ps.crit[7][lane] = roll; ps.crit[8][lane] = pitch; ps.crit[9][lane] = slope_c; }
     } else {
         // ---- obstacle + near-goal path critic + last point.  This warp idles while the pipeline fills: it first
         //      warms L2 with this block's share of the reachable terrain window.
         prefetch_terrain(p, st, tr, blockIdx.x, A.nblocks, lane, 32);
-        float obs = 0.0f, pf_near = 0.0f, lx = st.x, ly = st.y;
+        float obs = 0.0f, pf_near = 0.0f, lx = st.x, ly = st.y, px = st.x, py = st.y;
         auto chunk = [&](int c, auto fast_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
             const int sg = c % kPipeStages;
@@ -1061,6 +1077,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             for (int i = 0; i < kPipeChunk; ++i) {
                 const int t = c * kPipeChunk + i;
                 if (FAST || t < T) {
+                    if (kXC) { px = lx; py = ly; }
                     lx = ps.ring_b[sg][i][0][lane]; ly = ps.ring_b[sg][i][1][lane];
                     role_obstacle<!FAST>(p, st, ter, sc, t, lx, ly, pf_near, obs, oob);
                 }
@@ -1071,6 +1088,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         for (; c < nfast; ++c) chunk(c, FastTag<true>{});
         for (; c < nchunks; ++c) chunk(c, FastTag<false>{});
         ps.crit[2][lane] = obs; ps.crit[3][lane] = pf_near; ps.crit[4][lane] = lx; ps.crit[5][lane] = ly;
+        if (kXC) { ps.crit[10][lane] = px; ps.crit[11][lane] = py; }
     }
     ps.oob[role][lane] = oob;
     __syncthreads();
@@ -1084,7 +1102,11 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         SampleAcc a;
         a.speed = ps.crit[0][lane]; a.slope = ps.crit[1][lane]; a.obs = ps.crit[2][lane];
         a.pf_near = ps.crit[3][lane]; a.last_x = ps.crit[4][lane]; a.last_y = ps.crit[5][lane];
-        cost = sample_cost(p, sc, a, nullptr);
+        if (kXC) {
+            a.effort = ps.crit[6][lane]; a.roll = ps.crit[7][lane]; a.pitch = ps.crit[8][lane];
+            a.slope_c = ps.crit[9][lane]; a.pen_x = ps.crit[10][lane]; a.pen_y = ps.crit[11][lane];
+        }
+        cost = sample_cost(p, st, sc, a, nullptr);
         A.costs[(size_t)rover * K + k_local] = cost;
         for (int r = 0; r < 6; ++r) my_oob += (unsigned)ps.oob[r][lane];
         if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }
@@ -1144,10 +1166,11 @@ __global__ void __launch_bounds__(128) mppi_dump_kernel(const __grid_constant__ 
             sample_step<PROJ, true>(p, A.state, ter, sc, a, t + 1, u1, u2, d, (size_t)k * T + t + 1);
         }
     }
-    float cr[4];
-    const float cost = sample_cost(p, sc, a, cr);
+    float cr[4], cx[6];
+    const float cost = sample_cost<true>(p, A.state, sc, a, cr, cx);
     if (A.costs) A.costs[k] = cost;
     if (A.d.critics) { for (int i = 0; i < 4; ++i) A.d.critics[4 * k + i] = cr[i]; }
+    if (A.d.critics_ext) { for (int i = 0; i < 6; ++i) A.d.critics_ext[6 * k + i] = cx[i]; }
 }
 
 // Strided export for the visualiser: the driver shows every 50th sampled trajectory at every 10th step
@@ -1244,6 +1267,7 @@ __global__ void mppi_detmath_kernel(int fn, const float* x, float* y0, float* y1
     case 0: dm::sincosf_det(x[i], a, b); break;
     case 1: dm::sincos2pif_det(x[i], a, b); break;
     case 2: a = dm::logf_det(x[i]); break;
+    case 4: a = dm::atanf_det(x[i]); break;
     default: a = dm::expf_det(x[i]); break;
     }
     y0[i] = a;

@@ -1,6 +1,6 @@
 // mppi_kernels.cuh -- host-visible launch interface of the kernel translation units.
-// mppi_kernels.cu is compiled twice (STRICT and FAST arithmetic flavours, see mppi_device.cuh); each
-// compilation exports one set of launchers in its own namespace.
+// mppi_kernels.cu is compiled four times (STRICT and FAST arithmetic flavours, each without and with the optional
+// critics -DMPPI_XC, see mppi_device.cuh); each compilation exports one set of launchers in its own namespace.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -150,5 +150,7 @@ struct SimArgs {
 
 MPPI_DECLARE_LAUNCHERS(strict)
 MPPI_DECLARE_LAUNCHERS(fast)
+MPPI_DECLARE_LAUNCHERS(strict_xc)     // the same translation unit compiled with -DMPPI_XC (optional critics)
+MPPI_DECLARE_LAUNCHERS(fast_xc)
 
 }  // namespace mppi

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MPPI_B200_ABI_VERSION 2
+#define MPPI_B200_ABI_VERSION 3
 
 enum {
     MPPI_OK = 0,
@@ -81,6 +81,20 @@ typedef struct MppiParams {
     float horizon;          /* dt*v_max*T  MPPI_isaac.py:440 (host double -> float) */
     float target_speed;     /* v_max_linear MPPI_isaac.py:619 */
     int32_t input_model;    /* MPPI_INPUT_* */
+    /* ---- optional critics: weight 0 (the default) = off, the term is not evaluated and not added.  The first three
+     * are the reference's dormant critics (defined in critics_warp.py, their `costs[tid] +=` lines commented out or
+     * absent in _evaluate_trajectories_kernel :324,326); the last three are extensions with no reference counterpart
+     * (BASELINE configuration 5 names roll / pitch critics).  Cost order, all fp32 `+=` on the zeroed accumulator:
+     * orient, path, slope_path, slope(wheels), speed, obstacle, goal_angle, roll, pitch, effort. */
+    float cw_orient;        /* _path_orientation_critic  critics_warp.py:44-83 (commented coefficient 1.0, :324); T >= 2 */
+    float cw_slope_path;    /* _avoid_slope: stride-2 slope of the BODY path  critics_warp.py:131-166 (commented 50.5, :326) */
+    float cw_goal_angle;    /* _goal_angle_critic  critics_warp.py:5-41 (defined, never called); uses MppiState.goal_theta */
+    float goal_angle_radius;/* 0.5   critics_warp.py:33 */
+    float cw_roll;          /* extension: sum over even t of ((lw_z - rw_z) / (2 wheel_offset))^2   (tan of body roll) */
+    float cw_pitch;         /* extension: sum over even t of heading_z^2                            (sin of body pitch) */
+    float cw_effort;        /* extension: sum over t of u1^2 + u2^2 of the clamped sampled inputs */
+    int32_t reserved;       /* must be 0 (keeps sizeof(MppiParams) = 172 = 12 mod 16, the layout the kernels' parameter
+                               loads were tuned with) */
 } MppiParams;
 
 /* Terrain = DEM `Z_wp` + obstacle `costmap_wp` (MPPI_isaac.py:463-464), borrowed device pointers. */
@@ -123,6 +137,8 @@ typedef struct MppiDebugDump {
     int32_t *cm_ij;                         /* device [K*T*2] costmap cell (ix, iy) */
     float *critics;                         /* device [K*4]   path, slope, speed, obstacle (unweighted) */
     float *weights;                         /* device [K]     exp(-(c-min)/lambda) with the global min */
+    float *critics_ext;                     /* device [K*6]   orient, slope_path, goal_angle, roll, pitch, effort (unweighted;
+                                                              evaluated in the dump whatever their weights) */
 } MppiDebugDump;
 
 typedef struct MppiHandle MppiHandle;
@@ -262,7 +278,7 @@ int mppi_last_step_us(MppiHandle *h, float *us);
  * [nblocks * 32] uint64 (nblocks is returned through nblocks_out); NULL switches the stamps off (default). */
 int mppi_set_trace(MppiHandle *h, uint64_t *trace_dev, int32_t *nblocks_out);
 
-/* Test hook: evaluates the specified ("det") math on the device. fn: 0 sincos, 1 sincos(2*pi*u), 2 log, 3 exp.
+/* Test hook: evaluates the specified ("det") math on the device. fn: 0 sincos, 1 sincos(2*pi*u), 2 log, 3 exp, 4 atan.
  * x, y0, y1 are device pointers [n]. */
 int mppi_test_detmath(int32_t fn, const float *x_dev, float *y0_dev, float *y1_dev, int32_t n, void *stream);
 /* Test hook: Philox normals exactly as the production kernel draws them -> eps1/eps2 device [K*T]. */

@@ -150,4 +150,26 @@ static inline float dm_expf(float x)
     return (res * s1) * s2;
 }
 
+/* atan(x), any x (Cephes atanf: two range reductions + degree-4 odd polynomial in x^2); atan(+-inf) = +-pi/2,
+ * atan(NaN) = NaN.  Used by the goal-angle critic (critics_warp.py:37). */
+#define DM_A0 0x1.49e1a2p-4f
+#define DM_A1 -0x1.1c370ap-3f
+#define DM_A2 0x1.9924bep-3f
+#define DM_A3 -0x1.555454p-2f
+#define DM_TAN3PIO8 0x1.3504f4p+1f
+#define DM_TANPIO8 0x1.a8279ap-2f
+#define DM_PIO4 0x1.921fb6p-1f
+static inline float dm_atanf(float xx)
+{
+    float x = fabsf(xx), y = 0.0f;
+    if (x > DM_TAN3PIO8) { y = DM_PIO2_HI; x = -(1.0f / x); }
+    else if (x > DM_TANPIO8) { y = DM_PIO4; x = (x - 1.0f) / (x + 1.0f); }
+    float z = x * x;
+    float p = fmaf(DM_A0, z, DM_A1);
+    p = fmaf(p, z, DM_A2);
+    p = fmaf(p, z, DM_A3);
+    float r = y + fmaf(p * z, x, x);
+    return copysignf(r, xx);
+}
+
 #endif /* ORACLE_DET_MATH_H */

@@ -97,6 +97,7 @@ void oracle_detmath_eval(int32_t fn, const float *x, float *y0, float *y1, int32
         case 0: dm_sincosf(x[i], &y0[i], &y1[i]); break;
         case 1: dm_sincos2pif(x[i], &y0[i], &y1[i]); break;
         case 2: y0[i] = dm_logf(x[i]); break;
+        case 4: y0[i] = dm_atanf(x[i]); break;
         default: y0[i] = dm_expf(x[i]); break;
         }
     }
@@ -364,6 +365,76 @@ static float avoid_obstacle(const OrParams *p, Lookup *L, const float *traj, int
     return acc;
 }
 
+/* ---- optional critics (weight 0 by default) ---- */
+
+/* critics_warp.py:44-83: penalise a last segment that points away from the goal. */
+static float path_orientation(const OrParams *p, const OrState *st, const float *traj)
+{
+    int T = p->T;
+    if (T < 2) return 0.0f;                       /* the reference would read the previous sample's last point */
+    float x_diff = st->goal_x - st->x, y_diff = st->goal_y - st->y;
+    const float *pen = traj + 3 * (T - 2), *last = traj + 3 * (T - 1);
+    float x_diff2 = last[0] - pen[0], y_diff2 = last[1] - pen[1];
+    float sp = x_diff * x_diff2 + y_diff * y_diff2;
+    if (sp <= 0.0f) return -sp / (fabsf(x_diff) + fabsf(y_diff));
+    return 0.0f;
+}
+
+/* critics_warp.py:131-166: stride-2 slope of the body path (same form as the wheel critic, on trajectory[...].z) */
+static float avoid_slope_path(const OrParams *p, const float *traj)
+{
+    int T = p->T;
+    float total = 0.0f;
+    for (int i = 0; i < T - 3; i += 2) {
+        const float *c = traj + 3 * (i + 2), *q = traj + 3 * i;
+        float dz = c[2] - q[2];
+        float d = sqrtf((c[0] - q[0]) * (c[0] - q[0]) + (c[1] - q[1]) * (c[1] - q[1]));
+        float ratio = fabsf(dz / (d + p->slope_eps));
+        total += (1.0f + p->slope_gain * ratio) * (1.0f + p->slope_gain * ratio);
+    }
+    return total;
+}
+
+/* critics_warp.py:5-41: near the goal, |atan(dy/dx of the last segment) - goal_orientation| */
+static float goal_angle(const OrParams *p, const OrState *st, const MathMode *mm, const float *traj)
+{
+    int T = p->T;
+    if (T < 2) return 0.0f;
+    float dist = sqrtf((st->x - st->goal_x) * (st->x - st->goal_x) + (st->y - st->goal_y) * (st->y - st->goal_y));
+    if (dist < p->goal_angle_radius) {
+        const float *pen = traj + 3 * (T - 2), *last = traj + 3 * (T - 1);
+        float q = (last[1] - pen[1]) / (last[0] - pen[0]);
+        float a = mm->det ? dm_atanf(q) : atanf(q);
+        return fabsf(a - st->goal_theta);
+    }
+    return 0.0f;
+}
+
+/* extensions (no reference counterpart; BASELINE configuration 5 names roll / pitch critics) */
+static float roll_critic(const OrParams *p, const float *lw, const float *rw)
+{
+    float acc = 0.0f, track = 2.0f * p->wheel_offset;
+    for (int i = 0; i < p->T; i += 2) {
+        float r = (lw[3 * i + 2] - rw[3 * i + 2]) / track;
+        acc += r * r;
+    }
+    return acc;
+}
+
+static float pitch_critic(const OrParams *p, const float *heading)
+{
+    float acc = 0.0f;
+    for (int i = 0; i < p->T; i += 2) acc += heading[3 * i + 2] * heading[3 * i + 2];
+    return acc;
+}
+
+static float effort_critic(const OrParams *p, const float *u1, const float *u2)
+{
+    float acc = 0.0f;
+    for (int i = 0; i < p->T; ++i) acc += u1[i] * u1[i] + u2[i] * u2[i];
+    return acc;
+}
+
 int oracle_num_threads(void)
 {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
@@ -422,12 +493,29 @@ static void *worker_main(void *arg)
         float c_slope = avoid_slope_wheels(p, lw, rw);
         float c_speed = maximise_speed(p, st, v);
         float c_obs = avoid_obstacle(p, &L, traj, dump->cm_ij ? dump->cm_ij + 2 * o : NULL);
+        const int want_ext = dump->critics_ext != NULL;
+        float x_orient = (want_ext || p->cw_orient != 0.0f) ? path_orientation(p, st, traj) : 0.0f;
+        float x_slope = (want_ext || p->cw_slope_path != 0.0f) ? avoid_slope_path(p, traj) : 0.0f;
+        float x_angle = (want_ext || p->cw_goal_angle != 0.0f) ? goal_angle(p, st, &mm, traj) : 0.0f;
+        float x_roll = (want_ext || p->cw_roll != 0.0f) ? roll_critic(p, lw, rw) : 0.0f;
+        float x_pitch = (want_ext || p->cw_pitch != 0.0f) ? pitch_critic(p, hd) : 0.0f;
+        float x_effort = (want_ext || p->cw_effort != 0.0f) ? effort_critic(p, u1 + o, u2 + o) : 0.0f;
         float c = 0.0f;
+        if (p->cw_orient != 0.0f) c += p->cw_orient * x_orient;             /* :324 */
         c += p->cw_path * c_path;
+        if (p->cw_slope_path != 0.0f) c += p->cw_slope_path * x_slope;      /* :326 */
         c += p->cw_slope * c_slope;
         c += p->cw_speed * c_speed;
         c += p->cw_obs * c_obs;
+        if (p->cw_goal_angle != 0.0f) c += p->cw_goal_angle * x_angle;
+        if (p->cw_roll != 0.0f) c += p->cw_roll * x_roll;
+        if (p->cw_pitch != 0.0f) c += p->cw_pitch * x_pitch;
+        if (p->cw_effort != 0.0f) c += p->cw_effort * x_effort;
         cost[k] = c;
+        if (want_ext) {
+            float *e = dump->critics_ext + 6 * (size_t)k;
+            e[0] = x_orient; e[1] = x_slope; e[2] = x_angle; e[3] = x_roll; e[4] = x_pitch; e[5] = x_effort;
+        }
         if (dump->critics) {
             dump->critics[4 * k] = c_path; dump->critics[4 * k + 1] = c_slope;
             dump->critics[4 * k + 2] = c_speed; dump->critics[4 * k + 3] = c_obs;
@@ -477,7 +565,10 @@ int oracle_mppi_step(const OrParams *p, const OrTerrain *ter, const OrState *st,
     float S = 0.0f; double S64 = 0.0;
     float *wts = dump->weights ? dump->weights : (float *)malloc(sizeof(float) * K);
     for (int k = 0; k < K; ++k) {
-        float nc = cost[k] - m;
+        /* a NaN cost (possible only with the optional goal-angle / orientation critics: atan(0 / 0) for a sample that
+         * stands still) would poison every sum in the reference; the product gives such a sample zero weight and
+         * counts it (stats[4]) -- restated here so that the rule is checkable */
+        float nc = ((cost[k] != cost[k]) ? INFINITY : cost[k]) - m;
         wts[k] = m_exp(&mm, -nc / p->lambda);
         S += wts[k]; S64 += (double)wts[k];
     }

@@ -47,6 +47,15 @@ typedef struct OrParams {
     int32_t input_model;  /* 0: wheel inputs u1,u2 + first-order filter (_generate_inputs_kernel sampling_warp.py:54-92,
                              _convert_inputs_to_velocities :96-138); 1: velocity space (v, w) sampled directly
                              (_generate_velocities_kernel sampling_warp.py:10-48), no filter */
+    /* optional critics, weight 0 = not evaluated, not added.  Cost order: orient, path, slope_path, slope (wheels),
+     * speed, obstacle, goal_angle, roll, pitch, effort. */
+    float cw_orient;        /* _path_orientation_critic critics_warp.py:44-83 (commented `+=` at :324) */
+    float cw_slope_path;    /* _avoid_slope critics_warp.py:131-166 (commented `+=` at :326) */
+    float cw_goal_angle;    /* _goal_angle_critic critics_warp.py:5-41 (never called by the kernel) */
+    float goal_angle_radius;/* 0.5 critics_warp.py:33 */
+    float cw_roll;          /* extension (no reference): sum over even t of ((lw_z - rw_z) / (2 wheel_offset))^2 */
+    float cw_pitch;         /* extension: sum over even t of heading_z^2 */
+    float cw_effort;        /* extension: sum over t of u1^2 + u2^2 */
 } OrParams;
 
 typedef struct OrTerrain {
@@ -74,6 +83,7 @@ typedef struct OrDump {
     int32_t *dem_ij, *lw_ij, *rw_ij;      /* [K*T*2] (i, j) of projection_warp.py:39-40 / 338-339 / 345-346 */
     int32_t *cm_ij;                       /* [K*T*2] (ix, iy) of critics_warp.py:245-248 */
     float *critics;                       /* [K*4] path, slope, speed, obstacle (unweighted) */
+    float *critics_ext;                   /* [K*6] orient, slope_path, goal_angle, roll, pitch, effort (unweighted, always evaluated) */
     float *cost;                          /* [K] */
     float *weights;                       /* [K] */
 } OrDump;
@@ -96,7 +106,7 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 void oracle_philox_normals(uint64_t seed, uint64_t offset, uint32_t rover, uint32_t k0,
                            int32_t K, int32_t T, float *eps1, float *eps2, int32_t math);
 
-/* fn: 0 sincos, 1 sincos2pi, 2 log, 3 exp */
+/* fn: 0 sincos, 1 sincos2pi, 2 log, 3 exp, 4 atan */
 void oracle_detmath_eval(int32_t fn, const float *x, float *y0, float *y1, int32_t n);
 
 int oracle_mppi_step(const OrParams *p, const OrTerrain *ter, const OrState *st,

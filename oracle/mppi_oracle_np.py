@@ -26,6 +26,9 @@ DEFAULTS = dict(
     lam=0.3, r_wheels=1.2, filt_k=3.5, filt_a=0.96, opt_k=3.0, opt_a=0.92, wheel_offset=0.2,
     cw_path=100.5, cw_slope=50.5, cw_speed=0.5, cw_obs=25.0, lethal_thresh=0.99, lethal_penalty=100000.0,
     near_goal_cut=2.0, speed_eps=0.0001, pf_eps=1e-6, pf_near_gain=10.0, slope_eps=1e-6, slope_gain=5.0,
+    # optional critics (weight 0 = off): the reference's dormant ones, then the roll / pitch / effort extensions
+    cw_orient=0.0, cw_slope_path=0.0, cw_goal_angle=0.0, goal_angle_radius=0.5, cw_roll=0.0, cw_pitch=0.0,
+    cw_effort=0.0,
 )
 
 
@@ -286,6 +289,56 @@ def avoid_obstacle(p, ter, traj):
     return acc, cm_ij
 
 
+def path_orientation(p, x, y, gx, gy, traj):
+    """critics_warp.py:44-83."""
+    xd, yd = f32(gx) - f32(x), f32(gy) - f32(y)
+    xd2 = traj[:, -1, 0] - traj[:, -2, 0]
+    yd2 = traj[:, -1, 1] - traj[:, -2, 1]
+    sp = xd * xd2 + yd * yd2
+    return np.where(sp <= 0, -sp / (np.abs(xd) + np.abs(yd)), f32(0.0)).astype(np.float32)
+
+
+def avoid_slope_path(p, traj):
+    """critics_warp.py:131-166."""
+    N, T, _ = traj.shape
+    total = np.zeros(N, np.float32)
+    one = f32(1.0)
+    for i in range(0, T - 3, 2):
+        c, pv = traj[:, i + 2], traj[:, i]
+        dz = c[:, 2] - pv[:, 2]
+        d = np.sqrt((c[:, 0] - pv[:, 0]) * (c[:, 0] - pv[:, 0]) + (c[:, 1] - pv[:, 1]) * (c[:, 1] - pv[:, 1]))
+        ratio = np.abs(dz / (d + p.slope_eps))
+        total = total + (one + p.slope_gain * ratio) * (one + p.slope_gain * ratio)
+    return total
+
+
+def goal_angle(p, x, y, gx, gy, gtheta, traj):
+    """critics_warp.py:5-41 (libm atan; the C oracle's MATH_DET mode uses the specified atan instead)."""
+    x, y, gx, gy = f32(x), f32(y), f32(gx), f32(gy)
+    dist = np.sqrt((x - gx) * (x - gx) + (y - gy) * (y - gy))
+    if not dist < p.goal_angle_radius:
+        return np.zeros(traj.shape[0], np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = (traj[:, -1, 1] - traj[:, -2, 1]) / (traj[:, -1, 0] - traj[:, -2, 0])
+    return np.abs(np.arctan(q).astype(np.float32) - f32(gtheta))
+
+
+def roll_pitch_effort(p, lw, rw, heading, u1, u2):
+    """Extensions (no reference counterpart): see include/mppi_b200.h MppiParams.cw_roll / cw_pitch / cw_effort."""
+    N, T, _ = lw.shape
+    roll = np.zeros(N, np.float32)
+    pitch = np.zeros(N, np.float32)
+    effort = np.zeros(N, np.float32)
+    track = f32(2.0) * p.wheel_offset
+    for t in range(0, T, 2):
+        r = (lw[:, t, 2] - rw[:, t, 2]) / track
+        roll = roll + r * r
+        pitch = pitch + heading[:, t, 2] * heading[:, t, 2]
+    for t in range(T):
+        effort = effort + (u1[:, t] * u1[:, t] + u2[:, t] * u2[:, t])
+    return roll, pitch, effort
+
+
 def mppi_step(p: P, dem, half_width, costmap, state: dict, nom1, nom2, eps1, eps2, want_dump=True):
     """One full MPPI step (MPPI_isaac.py:505-720).  Returns a dict of every intermediate."""
     ter = Terrain(dem, half_width, costmap)
@@ -301,15 +354,28 @@ def mppi_step(p: P, dem, half_width, costmap, state: dict, nom1, nom2, eps1, eps
     c_slope = avoid_slope_wheels(p, ro["lw"], ro["rw"])
     c_speed = maximise_speed(p, st["x"], st["y"], st["goal_x"], st["goal_y"], v)
     c_obs, cm_ij = avoid_obstacle(p, ter, ro["traj"])
-    cost = np.zeros(p.K, np.float32)                              # critics_warp.py:325-329
+    x_orient = path_orientation(p, st["x"], st["y"], st["goal_x"], st["goal_y"], ro["traj"])
+    x_slope = avoid_slope_path(p, ro["traj"])
+    x_angle = goal_angle(p, st["x"], st["y"], st["goal_x"], st["goal_y"], st.get("goal_theta", 0.0), ro["traj"])
+    x_roll, x_pitch, x_effort = roll_pitch_effort(p, ro["lw"], ro["rw"], ro["heading"], u1, u2)
+    cost = np.zeros(p.K, np.float32)                              # critics_warp.py:324-329 (+ optional terms)
+    if p.cw_orient != 0:
+        cost = cost + p.cw_orient * x_orient
     cost = cost + p.cw_path * c_path
+    if p.cw_slope_path != 0:
+        cost = cost + p.cw_slope_path * x_slope
     cost = cost + p.cw_slope * c_slope
     cost = cost + p.cw_speed * c_speed
     cost = cost + p.cw_obs * c_obs
+    for wgt, val in ((p.cw_goal_angle, x_angle), (p.cw_roll, x_roll), (p.cw_pitch, x_pitch), (p.cw_effort, x_effort)):
+        if wgt != 0:
+            cost = cost + wgt * val
     # update, critics_warp.py:338-376 (race-free intent, old_files/run_mppi.py:222-226)
-    m = cost.min()
-    argmin = int(np.argmin(cost))
-    wts = np.exp(-(cost - m) / p.lam).astype(np.float32)
+    ceff = np.where(np.isnan(cost), np.float32(np.inf), cost)     # a NaN cost gets zero weight (product rule, stats[4])
+    m = ceff.min()
+    argmin = int(np.argmin(ceff))
+    with np.errstate(over="ignore"):
+        wts = np.exp(-(ceff - m) / p.lam).astype(np.float32)
     S = f32(0.0)
     for k in range(p.K):                                          # sequential fp32 atomic_add order 0..K-1
         S = f32(S + wts[k])
@@ -328,6 +394,7 @@ def mppi_step(p: P, dem, half_width, costmap, state: dict, nom1, nom2, eps1, eps
     p3.K, p3.proj = 1, 3
     sim = rollout(p3, ter, st["x"], st["y"], h0, ov, ow)
     out = dict(u1=u1, u2=u2, v=v, w=w, critics=np.stack([c_path, c_slope, c_speed, c_obs], axis=1), cost=cost,
+               critics_ext=np.stack([x_orient, x_slope, x_angle, x_roll, x_pitch, x_effort], axis=1),
                cm_ij=cm_ij, weights=wts, min_cost=float(m), argmin=argmin, weights_sum=float(S), nominal1=n1,
                nominal2=n2, opt_v=ov[0], opt_w=ow[0], sim_traj=sim["traj"][0], sim_heading=sim["heading"][0])
     out.update(ro)

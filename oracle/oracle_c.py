@@ -33,6 +33,8 @@ class OrParams(C.Structure):
         ("near_goal_cut", C.c_float), ("speed_eps", C.c_float), ("pf_eps", C.c_float),
         ("pf_near_gain", C.c_float), ("slope_eps", C.c_float), ("slope_gain", C.c_float),
         ("horizon", C.c_float), ("target_speed", C.c_float), ("input_model", C.c_int32),
+        ("cw_orient", C.c_float), ("cw_slope_path", C.c_float), ("cw_goal_angle", C.c_float),
+        ("goal_angle_radius", C.c_float), ("cw_roll", C.c_float), ("cw_pitch", C.c_float), ("cw_effort", C.c_float),
     ]
 
 
@@ -52,7 +54,7 @@ class OrState(C.Structure):
 class OrDump(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("u1", "u2", "v", "w", "traj", "heading", "lw", "rw",
-                 "dem_ij", "lw_ij", "rw_ij", "cm_ij", "critics", "cost", "weights")]
+                 "dem_ij", "lw_ij", "rw_ij", "cm_ij", "critics", "critics_ext", "cost", "weights")]
 
 
 class OrOut(C.Structure):
@@ -138,6 +140,7 @@ DEFAULTS = dict(
     cw_path=100.5, cw_slope=50.5, cw_speed=0.5, cw_obs=25.0,
     lethal_thresh=0.99, lethal_penalty=100000.0,
     near_goal_cut=2.0, speed_eps=0.0001, pf_eps=1e-6, pf_near_gain=10.0, slope_eps=1e-6, slope_gain=5.0,
+    goal_angle_radius=0.5,                # critics_warp.py:33; the optional critics' weights default to 0 (off)
 )
 
 
@@ -199,7 +202,7 @@ def mppi_step(params: OrParams, dem: np.ndarray, half_width: float, costmap: np.
     keep = {}
     names = []
     if dump is True:
-        names = list(_DUMP_SHAPES) + ["critics", "cost", "weights"]
+        names = list(_DUMP_SHAPES) + ["critics", "critics_ext", "cost", "weights"]
     elif dump:
         names = list(dump)
     for n in names:
@@ -208,6 +211,8 @@ def mppi_step(params: OrParams, dem: np.ndarray, half_width: float, costmap: np.
             a = np.zeros((K, T) if c == 1 else (K, T, c), dtype=dt)
         elif n == "critics":
             a = np.zeros((K, 4), dtype=np.float32)
+        elif n == "critics_ext":
+            a = np.zeros((K, 6), dtype=np.float32)
         else:
             a = np.zeros(K, dtype=np.float32)
         keep[n] = a

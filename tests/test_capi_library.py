@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound(capi):
 
 def test_abi_version_and_strerror(capi):
     lib = capi.lib()
-    assert lib.mppi_abi_version() == 2
+    assert lib.mppi_abi_version() == 3
     assert lib.mppi_strerror(0) == b"ok"
     assert b"invalid" in lib.mppi_strerror(-1)
     assert b"terrain" in lib.mppi_strerror(-3)
@@ -47,17 +47,18 @@ def test_default_params_are_the_reference_values(capi):
                lam=0.3, r_wheels=1.2, filt_k=3.5, filt_a=0.96, opt_k=3.0, opt_a=0.92, wheel_offset=0.2, cw_path=100.5,
                cw_slope=50.5, cw_speed=0.5, cw_obs=25.0, lethal_thresh=0.99, lethal_penalty=1e5, near_goal_cut=2.0,
                speed_eps=1e-4, pf_eps=1e-6, pf_near_gain=10.0, slope_eps=1e-6, slope_gain=5.0, horizon=9.0,
-               target_speed=2.0)
+               target_speed=2.0, cw_orient=0, cw_slope_path=0, cw_goal_angle=0, goal_angle_radius=0.5, cw_roll=0,
+               cw_pitch=0, cw_effort=0, reserved=0)
     for k, v in exp.items():
         assert got[k] == pytest.approx(v, rel=1e-6), k
 
 
 def test_struct_layouts_match_the_header(capi):
-    assert C.sizeof(capi.MppiParams) == 4 * 4 + 30 * 4 + 4      # + input_model (ABI version 2)
+    assert C.sizeof(capi.MppiParams) == 4 * 4 + 30 * 4 + 4 + 7 * 4 + 4      # + input_model (v2) + optional critics, reserved (v3)
     assert C.sizeof(capi.MppiState) == 48
     assert C.sizeof(capi.MppiTerrain) == 40
     assert C.sizeof(capi.MppiOutputs) == 8 * 8
-    assert C.sizeof(capi.MppiDebugDump) == 14 * 8
+    assert C.sizeof(capi.MppiDebugDump) == 15 * 8
 
 
 def test_argument_validation_without_a_device(capi):

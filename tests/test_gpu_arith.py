@@ -30,6 +30,8 @@ def test_det_math_matches_oracle_bitwise(L, oracle):
         2: np.concatenate([(rng.integers(1, 1 << 24, 600000).astype(np.float32) * np.float32(2.0 ** -24)),
                            rng.uniform(1e-30, 1e30, 400000).astype(np.float32)]),
         3: np.concatenate([np.linspace(-90, 10, 600001), -rng.exponential(5.0, 400000)]).astype(np.float32),
+        4: np.concatenate([np.linspace(-4, 4, 400001), rng.standard_cauchy(400000) * 10,
+                           np.array([0.0, -0.0, np.inf, -np.inf, 1e30, -1e-30])]).astype(np.float32),
     }
     for fn, x in cases.items():
         xd = dev(x)

@@ -49,6 +49,17 @@ def test_det_log_exp_accuracy(oracle):
     assert list(e) == [0.0, 0.0, 1.0, 1.0]          # flush below the normal range, by specification
 
 
+def test_det_atan_accuracy(oracle):
+    rng = np.random.default_rng(3)
+    x = np.concatenate([np.linspace(-4, 4, 400001), rng.standard_cauchy(400000) * 10,
+                        np.array([0.0, -0.0, np.inf, -np.inf, 1e30, -1e-30])]).astype(np.float32)
+    a, _ = oracle.detmath(4, x)
+    assert ulp_err(a, np.arctan(x.astype(np.float64))) <= 3.0      # Cephes atanf: ~2.7 ulp just above tan(pi/8)
+    assert np.array_equal(np.signbit(a[x == 0]), np.signbit(x[x == 0])) and a[np.isposinf(x)][0] == np.float32(np.pi / 2)
+    n, _ = oracle.detmath(4, np.array([np.nan], np.float32))
+    assert np.isnan(n[0])
+
+
 def test_philox_normals_statistics_and_replay(oracle):
     e1, e2 = oracle.philox_normals(42, 3, 4096, 100)
     n = e1.size

@@ -123,7 +123,7 @@ class GpuCore:
         K, T = self.K, self.T
         shapes = {"u1": (K, T), "u2": (K, T), "v": (K, T), "w": (K, T), "traj": (K, T, 3), "heading": (K, T, 3),
                   "lw": (K, T, 3), "rw": (K, T, 3), "dem_ij": (K, T, 2), "lw_ij": (K, T, 2), "rw_ij": (K, T, 2),
-                  "cm_ij": (K, T, 2), "critics": (K, 4), "weights": (K,)}
+                  "cm_ij": (K, T, 2), "critics": (K, 4), "weights": (K,), "critics_ext": (K, 6)}
         names = names or list(shapes)
         d = capi.MppiDebugDump()
         out = {}

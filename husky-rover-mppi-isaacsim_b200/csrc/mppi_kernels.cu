@@ -341,10 +341,15 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
     // 4. updated nominal = A / S  (critics_warp.py:363-376); keep the previous one for replay.  The smem copy of
     //    the OLD nominal is then overwritten with the filter drive u * k * (1 - a) of step 5.
     {
+        // No valid sample at all (every cost NaN / +inf, e.g. the whole fan of rollouts crossed no-data cells): S = 0
+        // and A / S would write a NaN nominal that poisons every later step -- the previous nominal is kept instead
+        // (the reference has no such case handling; stats[4] = K tells the caller).
+        const bool any_valid = S > 0.0f;
         const Recip rS = make_recip(S);
         const float oma = 1.0f - p.opt_a;
         for (int col = lane; col < 2 * T; col += 32) {
-            const float nv = fdiv(s.acc[col], rS);
+            const float old = (col < T) ? s.nom1[col] : s.nom2[col - T];
+            const float nv = any_valid ? fdiv(s.acc[col], rS) : old;
             const float drive = nv * p.opt_k * oma;
             s.acc[col] = nv;
             if (col < T) { prev1[col] = s.nom1[col]; nominal1[col] = nv; s.nom1[col] = drive; }
@@ -413,7 +418,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         stats[2] = S;
         stats[3] = __uint_as_float(oob_count);
         stats[4] = __uint_as_float(nan_count);
-        stats[5] = fdiv(S * S, S2);           // effective sample size
+        stats[5] = (S > 0.0f) ? fdiv(S * S, S2) : 0.0f;           // effective sample size
     }
     __syncwarp();
     MPPI_CLK(22);
@@ -768,8 +773,15 @@ enum { ROLE_NOISE0 = 0, ROLE_NOISE1 = 1, ROLE_CHAIN = 2, ROLE_WHEELS = 3, ROLE_F
 
 struct PipeSmem {
     unsigned long long full_u[kPipeStages], empty_u[kPipeStages];
-    unsigned long long full_a[kPipeStages], empty_a[kPipeStages];
-    unsigned long long full_b[kPipeStages], empty_b[kPipeStages];
+    unsigned long long empty_a[kPipeStages];
+    unsigned long long full_b[kPipeStages];
+    // What the CHAIN warp waits for is published as plain monotonic counters (st.release / ld.acquire at CTA scope)
+    // instead of mbarrier phases: an mbarrier try_wait costs ~90 cycles even when the phase completed long ago, twice
+    // per chunk on the one warp whose latency is the kernel's latency (14 % of its stall samples,
+    // profiles/r1_ncu_c2_strict_pipe.md).  A counter is read with one LDS, issued a whole chunk before it is needed,
+    // and one read usually covers several chunks because the filter runs up to kPipeStages chunks ahead.
+    int a_ready;                                      // chunks of ring A published by the filter warp
+    int b_done[2];                                    // chunks of ring B consumed by the wheel / obstacle warps
     float ring_u[kPipeStages][kPipeChunk][2][32];     // u1, u2
     float ring_a[kPipeStages][kPipeChunk][3][32];     // v, sin(w dt), cos(w dt)
     float ring_b[kPipeStages][kPipeChunk][8][32];     // x, y, n.xyz, cur.xyz
@@ -783,6 +795,22 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void st_release_cta(int* p, int v)
+{
+    asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+// one warp publishes "chunk count = v": every lane's ring stores happen-before lane 0's release through the warp sync
+__device__ __forceinline__ void warp_publish(int* counter, int v, int lane)
+{
+    __syncwarp();
+    if (lane == 0) st_release_cta(counter, v);
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
@@ -817,22 +845,20 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 }
 
 // projection_warp.py:8-48 on the shared-memory tile (indices proven in range by terrain_window_safe + the tile margins)
-__device__ __forceinline__ Quad corners_tile(const Terr& t, const float* tile, const DemTile& g, float x, float y)
+__device__ __forceinline__ Quad corners_tile(const Terr& t, const float* tile, const TileIdx& ti, float x, float y)
 {
-    int i, j;
-    dem_index(t, x, y, i, j);
-    const float* row = tile + ((j - g.j0) * g.w + (i - g.i0));
+    const unsigned rel = tile_rel(t, ti, x, y);
     Quad q;
-    q.q00 = row[0];
-    q.q01 = row[1];
-    q.q10 = row[g.w];
-    q.q11 = row[g.w + 1];
+    q.q00 = tile_at(tile, rel);
+    q.q01 = tile_at(tile, rel + 4u);
+    q.q10 = tile_at(tile, rel + ti.w4);
+    q.q11 = tile_at(tile, rel + ti.w4 + 4u);
     return q;
 }
 
 // chain role on the shared-memory DEM tile (3-D projection only)
 template <int PROJ>
-__device__ __forceinline__ void role_chain_tile(const MppiParams& p, const Terr& ter, const float* tile, const DemTile& g,
+__device__ __forceinline__ void role_chain_tile(const MppiParams& p, const Terr& ter, const float* tile, const TileIdx& g,
                                                 float& x, float& y, float3& prev, float v, float sn, float cs, float3& n,
                                                 float& dev)
 {
@@ -894,14 +920,17 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             tg.w = 0;
     }
 
+    const TileIdx tidx = make_tile_idx(tg.i0, tg.j0, tg.w, tg.h);
+
     float* nominal1 = A.nominal1 + (size_t)rover * T;
     float* nominal2 = A.nominal2 + (size_t)rover * T;
     if (tid == 0) {
         for (int i = 0; i < kPipeStages; ++i) {
             mbar_init(&ps.full_u[i], 32); mbar_init(&ps.empty_u[i], 32);
-            mbar_init(&ps.full_a[i], 32); mbar_init(&ps.empty_a[i], 32);
-            mbar_init(&ps.full_b[i], 32); mbar_init(&ps.empty_b[i], 64);
+            mbar_init(&ps.empty_a[i], 32);
+            mbar_init(&ps.full_b[i], 32);
         }
+        ps.a_ready = 0; ps.b_done[0] = 0; ps.b_done[1] = 0;
         mbar_init(&ps.tile_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -975,7 +1004,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                 }
             }
             mbar_arrive(&ps.empty_u[sg]);
-            mbar_arrive(&ps.full_a[sg]);
+            warp_publish(&ps.a_ready, c + 1, lane);
         }
         ps.crit[0][lane] = speed;
         if (kXC) ps.crit[6][lane] = effort;
@@ -992,22 +1021,30 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         if (lane == 0) trace_stamp(A, 2);
         const bool use_tile = (tg.w > 0) && (PROJ == MPPI_PROJ_3D) && (nfast > 0);
         if (use_tile) mbar_wait(&ps.tile_bar, 0);
+        if (lane == 0) trace_stamp(A, 25);                   // DEM tile landed
         // FAST: a full chunk whose cell indices need no clamping (terrain_window_safe) -> no per-step checks at all.
         // TILE: additionally the four corner gathers read the shared-memory DEM tile.
+        int a_seen = 0, b_seen = 0;          // last counter values this warp has read (monotonic, so stale is safe)
         auto chunk = [&](int c, auto fast_tag, auto tile_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
             constexpr bool TILE = decltype(tile_tag)::value;
             const int sg = c % kPipeStages;
-            const unsigned ph = (c / kPipeStages) & 1;
-            mbar_wait(&ps.full_a[sg], ph);
-            mbar_wait(&ps.empty_b[sg], ph ^ 1);
+            // chunk c of ring A published, and the slot of ring B released by both critic warps (they finished chunk
+            // c - kPipeStages); rarely taken after the pipeline has filled: the values were prefetched a chunk ago
+            for (unsigned spin = 0; a_seen <= c || b_seen < c + 1 - kPipeStages; ++spin) {
+                a_seen = ld_acquire_cta(&ps.a_ready);
+                b_seen = min(ld_acquire_cta(&ps.b_done[0]), ld_acquire_cta(&ps.b_done[1]));
+                if (spin > (1u << 24)) __trap();          // a broken pipeline must fail loudly, never hang the GPU
+            }
+            const int a_next = ld_acquire_cta(&ps.a_ready);          // for chunk c + 1: in flight during this chunk
+            const int b_next0 = ld_acquire_cta(&ps.b_done[0]), b_next1 = ld_acquire_cta(&ps.b_done[1]);
 #pragma unroll kChainUnroll
             for (int i = 0; i < kPipeChunk; ++i) {
                 const int t = c * kPipeChunk + i;
                 if (FAST || t < T) {
                     const float v = ps.ring_a[sg][i][0][lane];
                     const float sn = ps.ring_a[sg][i][1][lane], cs = ps.ring_a[sg][i][2][lane];
-                    if (TILE) role_chain_tile<PROJ>(p, ter, tile, tg, x, y, prev, v, sn, cs, n, dev);
+                    if (TILE) role_chain_tile<PROJ>(p, ter, tile, tidx, x, y, prev, v, sn, cs, n, dev);
                     else role_chain<PROJ, !FAST>(p, ter, x, y, prev, v, sn, cs, n, oob, dev);
                     float* o = &ps.ring_b[sg][i][0][lane];
                     o[0] = x; o[32] = y;
@@ -1019,6 +1056,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
             }
             mbar_arrive(&ps.empty_a[sg]);
             mbar_arrive(&ps.full_b[sg]);
+            a_seen = a_next; b_seen = min(b_next0, b_next1);
         };
         int c = 0;
         if (use_tile) { for (; c < nfast; ++c) chunk(c, FastTag<true>{}, FastTag<true>{}); }
@@ -1044,19 +1082,19 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                     const float* o = &ps.ring_b[sg][i][0][lane];
                     role_wheels<PROJ, !FAST, TILE>(p, ter, t, o[0], o[32], make_float3(o[64], o[96], o[128]),
                                                    make_float3(o[160], o[192], o[224]), lw_e, rw_e, slope, oob,
-                                                   tile, tg.w, tg.i0, tg.j0);
+                                                   tile, &tidx);
                     if (kXC) {
                         // optional critics of the even steps: lw_e / rw_e now hold this step's wheel points; the
                         // body height is re-interpolated here (the chain role does not need it)
                         int bi, bj, dummy = 0;
-                        const Quad q = TILE ? corners_tile(ter, tile, tg, o[0], o[32])
+                        const Quad q = TILE ? corners_tile(ter, tile, tidx, o[0], o[32])
                                             : corners<!FAST>(ter, o[0], o[32], bi, bj, dummy);
                         extras_even(p, t, o[0], o[32], bilinear(o[0], o[32], q, ter.rres), lw_e.z, rw_e.z, o[224],
                                     roll, pitch, slope_c, ctr_e);
                     }
                 }
             }
-            mbar_arrive(&ps.empty_b[sg]);
+            warp_publish(&ps.b_done[0], c + 1, lane);
         };
         int c = 0;
         if (use_tile) { for (; c < nfast; ++c) chunk(c, FastTag<true>{}, FastTag<true>{}); }
@@ -1082,7 +1120,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
                     role_obstacle<!FAST>(p, st, ter, sc, t, lx, ly, pf_near, obs, oob);
                 }
             }
-            mbar_arrive(&ps.empty_b[sg]);
+            warp_publish(&ps.b_done[1], c + 1, lane);
         };
         int c = 0;
         for (; c < nfast; ++c) chunk(c, FastTag<true>{});

@@ -124,12 +124,24 @@ static inline int32_t clampi(int32_t v, int32_t lo, int32_t hi, int32_t *oob)
     return v;
 }
 
+/* wp.int(x) = C cast, truncation toward zero.  The cast is undefined in C for NaN and for values outside int32 (a
+ * rollout that touched a no-data cell of the DEM); the GPU conversion is defined (NaN -> 0, saturation), and that
+ * definition is restated here so that such runs are comparable instead of crashing the checker. */
+static inline int32_t f2i(float v)
+{
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)v;
+}
+static inline int32_t negi(int32_t v) { return (int32_t)(0u - (uint32_t)v); }   /* two's-complement wrap, as the GPU's integer negate */
+
 /* projection_warp.py:39-40 -- cell index of (x, y).  x_min = y_min = -half_width (MPPI_isaac.py:584-585). */
 static inline void dem_index(const OrTerrain *t, float x, float y, int32_t *i, int32_t *j)
 {
     float x_min = -t->half_width, y_min = -t->half_width;
-    *i = (int32_t)((x - x_min) / t->res);
-    *j = -(int32_t)((y + y_min) / t->res);
+    *i = f2i((x - x_min) / t->res);
+    *j = negi(f2i((y + y_min) / t->res));
 }
 
 /* projection_warp.py:8-48 */
@@ -354,7 +366,7 @@ static float avoid_obstacle(const OrParams *p, Lookup *L, const float *traj, int
     for (int i = 0; i < p->T; ++i) {
         float idx_x = (traj[3 * i] + t->half_width) / t->cres;
         float idx_y = (-traj[3 * i + 1] + t->half_width) / t->cres;
-        int32_t ix = (int32_t)idx_x, iy = (int32_t)idx_y;
+        int32_t ix = f2i(idx_x), iy = f2i(idx_y);
         if (cm_ij) { cm_ij[2 * i] = ix; cm_ij[2 * i + 1] = iy; }
         ix = clampi(ix, 0, t->cms - 1, &L->oob);
         iy = clampi(iy, 0, t->cms - 1, &L->oob);
@@ -581,6 +593,9 @@ int oracle_mppi_step(const OrParams *p, const OrTerrain *ter, const OrState *st,
             d1 += (double)wts[k] * (double)u1[(size_t)k * T + t];
             d2 += (double)wts[k] * (double)u2[(size_t)k * T + t];
         }
+        /* no valid sample (every cost NaN / +inf): the product keeps the previous nominal (the reference would
+         * store 0 / 0) */
+        if (!(S > 0.0f)) { a1 = nom1[t]; a2 = nom2[t]; }
         out->nominal1[t] = a1; out->nominal2[t] = a2;
         if (out->nominal1_f64) out->nominal1_f64[t] = d1 / S64;
         if (out->nominal2_f64) out->nominal2_f64[t] = d2 / S64;

@@ -385,6 +385,8 @@ def mppi_step(p: P, dem, half_width, costmap, state: dict, nom1, nom2, eps1, eps
     for k in nz:                                                  # zero weights add exactly +0
         n1 = n1 + wts[k] * u1[k] / S
         n2 = n2 + wts[k] * u2[k] / S
+    if not S > 0:                                                 # no valid sample: the product keeps the nominal
+        n1, n2 = np.asarray(nom1, np.float32).copy(), np.asarray(nom2, np.float32).copy()
     if p.input_model == 1:
         ov, ow = n1[None, :].copy(), n2[None, :].copy()
     else:

@@ -324,3 +324,75 @@ def test_shared_memory_dem_tile_changes_no_bit(oracle, monkeypatch):
     ref = oracle.mppi_step(oracle.make_params(K=K, T=T, lam=30.0), dem, hw, cm, default_state(), z, z, eps[0], eps[1],
                            dump=["cost"])
     assert np.array_equal(outs[0][0], ref.dump["cost"])
+
+
+def _dem_with_hole(ahead, lateral, rows, cols):
+    dem, cm, hw = terrain("C1")
+    st = default_state()
+    dem = dem.copy()
+    res = 2 * hw / dem.shape[0]
+    i = int((st["x"] + ahead + hw) / res)                 # `ahead` metres in front of the rover (heading +x)
+    j = int((hw - (st["y"] + lateral)) / res)
+    dem[j:j + rows, i:i + cols] = np.nan
+    return dem, cm, hw, st
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["mono", "pipe"])
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_nan_cells_in_the_dem_are_survivable(oracle, variant, math):
+    """Real DEMs carry no-data cells.  A rollout that touches one gets NaN normals / positions; the reference would
+    then gather out of bounds (it has no checks at all).  Here the step must neither fault (the shared-memory tile
+    clamps its byte offset, the global path its indices) nor let the NaN into the update: such samples get zero
+    weight and are counted in stats[4]; everything else stays finite.  STRICT: same NaN set and same bits as the
+    oracle, over three closed-loop iterations (the controller steers away from the hole by itself)."""
+    import torch
+    from mppi_b200.core import Core
+    K, T = 2048, 60
+    dem, cm, hw, st = _dem_with_hole(2.5, 0.3, 3, 3)
+    core = Core(K, T, math=math, variant=variant)
+    core.set_terrain(torch.from_numpy(dem).cuda(), hw, torch.from_numpy(cm).cuda())
+    n1 = n2 = np.full(T, 0.6, np.float32)
+    core.set_nominal(n1, n2)
+    seen = 0
+    for it in range(3):
+        core.step(state_struct(st), seed=3, offset=it)
+        torch.cuda.synchronize()
+        s = core.read_stats()
+        costs = core.costs[0].cpu().numpy()
+        u1 = core.optimal_u1[0].cpu().numpy()
+        assert s["nan"] == int(np.isnan(costs).sum()) and s["nan"] < K
+        assert np.all(np.isfinite(u1)) and np.all(np.isfinite(core.optimal_v[0].cpu().numpy()))
+        assert np.isfinite(s["min_cost"]) and not np.isnan(costs[s["argmin"]])
+        seen += s["nan"]
+        if math == "strict":
+            e1, e2 = oracle.philox_normals(3, it, K, T)
+            r = oracle.mppi_step(oracle.make_params(K=K, T=T), dem, hw, cm, st, n1, n2, e1, e2, dump=["cost"],
+                                 nthreads=8)
+            ref = r.dump["cost"]
+            assert np.array_equal(np.isnan(costs), np.isnan(ref))
+            assert np.array_equal(costs[~np.isnan(ref)], ref[~np.isnan(ref)]) and s["argmin"] == r.argmin
+            assert close(u1, r.nominal1, 1e-2) < RTOL
+            n1, n2 = u1, core.optimal_u2[0].cpu().numpy()
+    assert seen > 100
+    core.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["mono", "pipe"])
+def test_no_valid_sample_keeps_the_nominal(variant):
+    """Every rollout crosses a wall of no-data cells: no sample has a finite cost, the weights sum to zero.  The
+    nominal must be kept (the reference would store 0 / 0), the command comes from it, stats[4] = K."""
+    import torch
+    from mppi_b200.core import Core
+    K, T = 1024, 60
+    dem, cm, hw, st = _dem_with_hole(1.5, 0.8, 16, 3)
+    core = Core(K, T, variant=variant)
+    core.set_terrain(torch.from_numpy(dem).cuda(), hw, torch.from_numpy(cm).cuda())
+    n = np.full(T, 0.6, np.float32)
+    core.set_nominal(n, n)
+    core.step(state_struct(st), seed=3, offset=0)
+    torch.cuda.synchronize()
+    s = core.read_stats()
+    assert s["nan"] == K and s["weights_sum"] == 0.0 and s["ess"] == 0.0
+    assert np.array_equal(core.optimal_u1[0].cpu().numpy(), n) and np.array_equal(core.optimal_u2[0].cpu().numpy(), n)
+    assert np.all(np.isfinite(core.optimal_v[0].cpu().numpy())) and core.optimal_v[0, 0].item() > 0
+    core.close()

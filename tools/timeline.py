@@ -108,6 +108,18 @@ def main():
         if vals:
             cyc[name] = float(np.median(vals))
     out["last_block_update_cycles"] = cyc
+    x = rel[:, :, 25] - rel[:, :, 2]
+    out["phases_us"]["tile_landed_after_rollout_start"] = {"min": float(np.nanmin(x)), "median": float(np.nanmedian(x)),
+                                                           "max": float(np.nanmax(x))}
+    # is slowness tied to the block (= its samples), to the SM, or random?  correlation of per-block duration across reps
+    durb = rel[:, :, 3] - rel[:, :, 25]
+    z = durb - np.nanmean(durb, axis=1, keepdims=True)
+    cc = np.corrcoef(z[::2].mean(0), z[1::2].mean(0))[0, 1]
+    out["block_duration_corr_even_vs_odd_reps"] = float(cc)
+    slow = np.argsort(-np.nanmean(durb, axis=0))[:6]
+    out["slowest_blocks"] = [{"block": int(b), "smid": int(rel[0, b, 7]), "mean_us": float(np.nanmean(durb[:, b]))} for b in slow]
+    fast = np.argsort(np.nanmean(durb, axis=0))[:6]
+    out["fastest_blocks"] = [{"block": int(b), "smid": int(rel[0, b, 7]), "mean_us": float(np.nanmean(durb[:, b]))} for b in fast]
     dur = rel[:, :, 3] - rel[:, :, 2]
     out["rollout_us_per_block"] = {"min": float(np.nanmin(dur)), "median": float(np.nanmedian(dur)),
                                    "max": float(np.nanmax(dur)), "per_step_ns_median": float(np.nanmedian(dur) * 1e3 / w.T)}

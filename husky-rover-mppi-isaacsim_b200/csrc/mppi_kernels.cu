@@ -231,16 +231,22 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
     } else {
         // ---- few partials (latency regime): one warp, no block barrier anywhere
         if (tid >= 32) return;
-        // 1. global min / argmin (ties -> lowest sample id); at most four partials per lane
+        // 1. global min / argmin (ties -> lowest sample id); at most four partials per lane.  ALL header loads are
+        //    issued before the first comparison: each is an L2 round trip (~700 cycles for a line another SM has just
+        //    written), and interleaved with the comparisons they ran one after the other (3700 cycles for this step
+        //    in the kernel-internal timeline; one round trip is enough).
         float mb4[4];
+        int kb4[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int b = lane + 32 * q;
-            mb4[q] = CUDART_INF_F;
-            if (b < n) {
-                mb4[q] = __ldcg(parts + (size_t)b * stride);
-                pair_min(M, arg, mb4[q], __float_as_int(__ldcg(parts + (size_t)b * stride + 2)));
-            }
+            const float* hp = parts + (size_t)min(lane + 32 * q, n - 1) * stride;      // clamped: no branch around the loads
+            mb4[q] = __ldcg(hp);
+            kb4[q] = __float_as_int(__ldcg(hp + 2));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (lane + 32 * q < n) pair_min(M, arg, mb4[q], kb4[q]);
+            else mb4[q] = CUDART_INF_F;
         }
         warp_min(M, arg);
         MPPI_CLK(17);
@@ -270,21 +276,29 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         float acc[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = 0.0f;
-        for (int e = 0; e < cnt; ++e) {
-            const float* pb = parts + (size_t)s.list_i[e] * stride;
-            const float sc = s.list_w[e];
-            float v[8];
+        // two kept partials per pass: their loads share one L2 round trip; the additions keep the partial order
+        for (int e = 0; e < cnt; e += 2) {
+            const bool two = e + 1 < cnt;
+            const float* pb0 = parts + (size_t)s.list_i[e] * stride;
+            const float* pb1 = two ? parts + (size_t)s.list_i[e + 1] * stride : pb0;
+            const float sc0 = s.list_w[e], sc1 = two ? s.list_w[e + 1] : 0.0f;
+            float v0[8], v1[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int col = col0 + lane + 32 * q;
-                v[q] = (col < 2 * T) ? __ldcg(pb + kPartialHeader + col) : 0.0f;
+                v0[q] = (col < 2 * T) ? __ldcg(pb0 + kPartialHeader + col) : 0.0f;
+                v1[q] = (col < 2 * T) ? __ldcg(pb1 + kPartialHeader + col) : 0.0f;
             }
-            if (col0 == 0) {
-                S += __ldcg(pb + 1) * sc;
-                S2 += __ldcg(pb + 3) * sc * sc;
-            }
+            float s0 = 0.0f, q0 = 0.0f, s1 = 0.0f, q1 = 0.0f;
+            if (col0 == 0) { s0 = __ldcg(pb0 + 1); q0 = __ldcg(pb0 + 3); s1 = __ldcg(pb1 + 1); q1 = __ldcg(pb1 + 3); }
+            if (col0 == 0) { S += s0 * sc0; S2 += q0 * sc0 * sc0; }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] += v[q] * sc;
+            for (int q = 0; q < 8; ++q) acc[q] += v0[q] * sc0;
+            if (two) {
+                if (col0 == 0) { S += s1 * sc1; S2 += q1 * sc1 * sc1; }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += v1[q] * sc1;
+            }
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -398,6 +412,7 @@ __device__ void combine_and_finalize(const MppiParams& p, const MppiState& st, c
         __syncwarp();
         MPPI_CLK(21);
         const Recip rw = make_recip(p.r_wheels);
+#pragma unroll 4
         for (int t = lane; t < T; t += 32) {
             const float l = s.nom1[t], r = s.nom2[t];
             const float v = clampf((l + r) / 2.0f, p.v_min, p.v_max);

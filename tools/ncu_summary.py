@@ -2,6 +2,9 @@
 """Turns an `ncu --set full --import-source on` report into the markdown summary committed under profiles/.
 
   python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_<what>.md
+  python tools/ncu_summary.py gpurun_out/prof.ncu-rep --counters C2_strict profiles/rNN_<what>.md
+      (additionally records warp-instructions / DRAM bytes per launch of the first captured launch under that key in
+       profiles/kernel_counters.json, which bench.py reads for roofline.issue / roofline.traffic)
 
 Runs here (no GPU needed: `ncu -i` only reads the report).
 """
@@ -39,10 +42,30 @@ def ncu_csv(rep, page):
     return list(csv.reader(io.StringIO(out)))
 
 
+def update_counters(raw, key, source):
+    import json
+    import os
+    hdr = raw[0]
+    d = dict(zip(hdr, raw[2]))
+    f = lambda k: float(d[k].replace(",", "")) if d.get(k) else 0.0                       # noqa: E731
+    units = dict(zip(hdr, raw[1]))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dram = sum(f(k) * scale.get(units.get(k, "byte"), 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "kernel_counters.json")
+    allc = json.load(open(path)) if os.path.exists(path) else {}
+    allc[key] = {"warp_inst_per_launch": f("smsp__inst_executed.sum"), "dram_bytes_per_launch": dram,
+                 "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                 "l1_hit_pct": f("l1tex__t_sector_hit_rate.pct"), "kernel": d.get("Kernel Name"),
+                 "source": f"{source} (ncu --set full, first captured launch)"}
+    json.dump(allc, open(path, "w"), indent=1)
+
+
 def main():
     rep = sys.argv[1]
     raw = ncu_csv(rep, "raw")
     hdr, units = raw[0], raw[1]
+    if len(sys.argv) >= 5 and sys.argv[2] == "--counters":
+        update_counters(raw, sys.argv[3], sys.argv[4])
     print(f"# ncu summary of `{rep.split('/')[-1]}`\n")
     print("`ncu --set full --clock-control none --import-source on` (one replayed launch per row; times under the "
           "profiler are cold-cache and serialised and are NOT bench numbers).\n")

@@ -482,13 +482,37 @@ __device__ void loop_advance(const FusedArgs& A, const MppiState& st, const floa
     if (!far) A.loop.ctl[1] = 1;
 }
 
+// Running minimum of the block minima published so far in this launch (counters[3] of the rover), as an order-reversed
+// unsigned key so that atomicMax keeps the SMALLEST cost and 0 (the re-armed value) means "nothing published yet".
+// A block whose own minimum is more than 90 lambda above ANY already published minimum will get the scale
+// exp(-(m_b - M) / lambda) == 0 in the final fold whatever the other blocks do (M can only be lower still; the exp is
+// flushed to zero below -87), i.e. its partial is never read: it skips the exponentials, the regeneration of its best
+// sample's inputs and the store of its A rows -- with lambda = 0.3 that is all but one or two blocks, including,
+// almost always, the block that finishes last and sits on the critical path.  The result does not depend on which
+// blocks skipped: a skipped partial is exactly one that the fold drops.
+__device__ __forceinline__ unsigned min_key(float c)
+{
+    const unsigned u = __float_as_uint(c);
+    return ~((u & 0x80000000u) ? ~u : (u | 0x80000000u));
+}
+__device__ __forceinline__ float min_key_cost(unsigned key)
+{
+    const unsigned o = ~key;
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ bool partial_is_dead(const MppiParams& p, float m_b, unsigned snapshot_key)
+{
+    return snapshot_key != 0u && (m_b - min_key_cost(snapshot_key)) > 90.0f * p.lambda;
+}
+
 // ------------------------------------------------------------------ phases 2 + 3, shared by both fused kernels
 // Every thread of the block calls this.  `valid` threads own one sample each (local index `k_in_block`, cost
 // `cost`); `spb` = samples per block.  INJECT: u is re-read from the injected noise instead of regenerated.
 template <bool INJECT>
 __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState& st, const NoiseKey& nk, const Smem& s,
                                              int rover, int spb, bool valid, int k_in_block, float cost,
-                                             unsigned my_oob, unsigned my_nan, float* nominal1, float* nominal2)
+                                             unsigned my_oob, unsigned my_nan, float* nominal1, float* nominal2,
+                                             unsigned snapshot_key /* thread 0: counters[3] read a little earlier */)
 {
     const MppiParams& p = A.p;
     const UBounds ub = make_ubounds(p);
@@ -502,30 +526,47 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
     int arg_b = valid ? (int)kg : 0x7fffffff;
     float w = 0.0f, s_b, s2_b;
     int n_e;
+    bool dead_partial;
     if (tid == 0) trace_stamp(A, 8);
     if (spb == 32) {
         // all samples of the block live in warp 0: warp-level reductions, one barrier to publish the list
         if (tid < 32) {
             warp_min(m_b, arg_b);
-            if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));   // critics_warp.py:346-347
-            s_b = warp_sum(w);
-            s2_b = warp_sum(w * w);
-            const unsigned mask = __ballot_sync(0xffffffffu, w > 0.0f);
-            if (w > 0.0f) {
-                const int pos = __popc(mask & ((1u << tid) - 1u));
-                s.list_i[pos] = k_in_block;
-                s.list_w[pos] = w;
+            if (tid == 0) atomicMax(&A.counters[rover * kCounterStride + 3], min_key(m_b));
+            const bool dead = partial_is_dead(p, m_b, __shfl_sync(0xffffffffu, snapshot_key, 0));
+            unsigned mask = 0u;
+            s_b = 0.0f; s2_b = 0.0f;
+            if (!dead) {
+                if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));   // critics_warp.py:346-347
+                s_b = warp_sum(w);
+                s2_b = warp_sum(w * w);
+                mask = __ballot_sync(0xffffffffu, w > 0.0f);
+                if (w > 0.0f) {
+                    const int pos = __popc(mask & ((1u << tid) - 1u));
+                    s.list_i[pos] = k_in_block;
+                    s.list_w[pos] = w;
+                }
             }
-            if (tid == 0) { s.red_i[62] = __popc(mask); s.red_f[0] = m_b; s.red_f[1] = s_b; s.red_f[2] = s2_b; s.red_i[0] = arg_b; }
+            if (tid == 0) {
+                s.red_i[62] = __popc(mask); s.red_f[0] = m_b; s.red_f[1] = s_b; s.red_f[2] = s2_b; s.red_i[0] = arg_b;
+                s.red_i[61] = dead;
+            }
         }
         __syncthreads();
         n_e = s.red_i[62]; m_b = s.red_f[0]; s_b = s.red_f[1]; s2_b = s.red_f[2]; arg_b = s.red_i[0];
+        dead_partial = s.red_i[61] != 0;
     } else {
+        if (tid == 0) s.red_i[60] = (int)snapshot_key;          // visible to the block after block_min's barriers
         block_min(m_b, arg_b, s);
-        if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));       // critics_warp.py:346-347
-        s_b = w; s2_b = w * w;
-        block_sum2(s_b, s2_b, s);
-        n_e = block_compact(w > 0.0f, k_in_block, w, 0, s);
+        if (tid == 0) atomicMax(&A.counters[rover * kCounterStride + 3], min_key(m_b));
+        dead_partial = partial_is_dead(p, m_b, (unsigned)s.red_i[60]);      // block-uniform
+        s_b = 0.0f; s2_b = 0.0f; n_e = 0;
+        if (!dead_partial) {
+            if (valid && cost < CUDART_INF_F) w = fexp(fdiv(-(cost - m_b), p.lambda));   // critics_warp.py:346-347
+            s_b = w; s2_b = w * w;
+            block_sum2(s_b, s2_b, s);
+            n_e = block_compact(w > 0.0f, k_in_block, w, 0, s);
+        }
         __syncthreads();
     }
     if (tid == 0) trace_stamp(A, 10);
@@ -541,7 +582,7 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
         if (!flat) { part_local[idx] = v; return; }
         for (int r = 0; r < ndst; ++r) A.peers.x[r][xoff + idx] = v;
     };
-    {
+    if (!dead_partial) {
         const int P = (T + 1) >> 1;                       // step pairs
         const int G = (B >= 2 * P && n_e > 1) ? B / P : 1;   // entry groups working in parallel
         const int g = tid / P, pr0 = tid - g * P;
@@ -664,6 +705,7 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
         A.counters[rover * kCounterStride + 0] = 0u;
         A.counters[rover * kCounterStride + 1] = 0u;
         A.counters[rover * kCounterStride + 2] = 0u;
+        A.counters[rover * kCounterStride + 3] = 0u;
     }
 }
 
@@ -759,7 +801,9 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
         if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }   // a NaN rollout gets zero weight
     }
     if (tid == 0) { trace_stamp(A, 3); trace_stamp(A, 4); }
-    block_update<INJECT>(A, st, nk, s, rover, B, valid, tid, cost, my_oob, my_nan, nominal1, nominal2);
+    // snapshot of the running minimum of the blocks that already finished (see partial_is_dead); any value is safe
+    const unsigned snap = (tid == 0) ? __ldcg(&A.counters[rover * kCounterStride + 3]) : 0u;
+    block_update<INJECT>(A, st, nk, s, rover, B, valid, tid, cost, my_oob, my_nan, nominal1, nominal2, snap);
 }
 
 // ------------------------------------------------------------------ warp-specialised fused kernel (latency regime)
@@ -1144,6 +1188,15 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         if (kXC) { ps.crit[10][lane] = px; ps.crit[11][lane] = py; }
     }
     ps.oob[role][lane] = oob;
+    // thread 0 (a noise warp, done long before the chain) reads the running minimum of the blocks that have already
+    // finished while it waits for the other roles: the L2 round trip is off the critical path (see partial_is_dead)
+    unsigned snap = 0u;
+    if (tid == 0) {
+        // ... but not too early: thread 0 idles until the critic warps are within one chunk of the end, so that the
+        // snapshot covers the blocks that finished up to ~1 us before this one
+        for (unsigned spin = 0; ld_acquire_cta(&ps.b_done[1]) < nchunks - 1 && spin < (1u << 16); ++spin) __nanosleep(128);
+        snap = __ldcg(&A.counters[rover * kCounterStride + 3]);
+    }
     __syncthreads();
     if (tid == 0) trace_stamp(A, 4);
 
@@ -1164,7 +1217,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         for (int r = 0; r < 6; ++r) my_oob += (unsigned)ps.oob[r][lane];
         if (cost != cost) { my_nan = 1; cost = CUDART_INF_F; }
     }
-    block_update<INJECT>(A, st, nk, s, rover, 32, owner, lane, cost, my_oob, my_nan, nominal1, nominal2);
+    block_update<INJECT>(A, st, nk, s, rover, 32, owner, lane, cost, my_oob, my_nan, nominal1, nominal2, snap);
 }
 
 // ------------------------------------------------------------------ rank-partial combine (multi-GPU epilogue)

@@ -15,7 +15,7 @@ __host__ __device__ inline int partial_stride(int T) { return kPartialHeader + 2
 
 constexpr int kMaxBlock = 256;        // threads per block upper bound
 constexpr int kStatsStride = 8;       // floats per rover in the stats buffer
-constexpr int kCounterStride = 4;     // uints per rover: {ticket, oob, nan, 0}
+constexpr int kCounterStride = 4;     // uints per rover: {ticket, oob, nan, running-minimum key of the block minima}
 
 // Peer exchange of the sample-sharded multi-GPU step (one process per GPU; buffers mapped with CUDA IPC).
 // Rank r owns x[r]: [2 parities][world][nblocks][partial_stride(T)] floats and f[r]: [2][world] arrival flags.  EVERY

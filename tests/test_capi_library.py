@@ -101,3 +101,20 @@ def test_product_never_imports_the_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "oracle_c" not in src, f
                 if f.endswith((".cu", ".cuh")):
                     assert "oracle/" not in src.replace("oracle/mppi_oracle.c", "").replace("oracle/det_math.h", ""), f
+
+
+def test_integration_md_binding_stub_matches_the_abi(capi):
+    """INTEGRATION.md shows the ctypes binding a maintainer of the reference would add; its structures must be the
+    header's (same field order and sizes), or the stub would silently corrupt arguments."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "INTEGRATION.md")).read()
+    ns = {"C": C}
+    for name in ("MppiParams", "MppiTerrain", "MppiState"):
+        m = re.search(r"class %s\(C\.Structure\):.*?\n\n" % name, src, re.S)
+        assert m, name
+        exec(m.group(0), ns)
+        mine, theirs = getattr(capi, name), ns[name]
+        assert C.sizeof(mine) == C.sizeof(theirs), name
+        norm = lambda n: "lam" if n == "lambda_" else n                                  # noqa: E731
+        assert [(norm(n), t) for n, t in theirs._fields_] == [(n, t) for n, t in mine._fields_], name

@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- MPPI hot-path benchmark (one JSON line on stdout, contract in the task statement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C5] [--math strict|fast]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1..C5] [--math strict|fast] [--critics auto|reference|ext]
+                  [--exchange p2p|nccl] [--variant auto|mono|pipe]
   python bench.py --impl reference ...        # CPU port of the reference path on the host cores
+  tools/ab.sh <other libmppi_b200.so> [bench args]   # same-node A/B of two builds (MPPI_B200_LIB selects the library)
 
 A "step" is one full control iteration (sample -> wheel filter -> rollout on the DEM -> critics -> softmax
 update -> (v*, w*)) of ONE fused kernel launch over synthetic terrain of the BASELINE.json shape.
 N = 1 runs BASELINE config 2 (K = 4096, T = 100, 1500^2 DEM, 750^2 costmap).  N > 1 keeps that per-GPU
-workload (weak scaling): one logical controller with N x 4096 samples, sample-sharded, whose only exchange
-is an all-gather of the 816-byte softmax partial followed by the same deterministic combine on every rank.
+workload (weak scaling): one logical controller with N x 4096 samples, sample-sharded, whose only exchange is the
+816-byte softmax partial per block / rank: stored into every rank's buffer over NVLink peer memory inside the fused
+launch (default), or one NCCL all-gather + combine kernel (--exchange nccl); the same deterministic fold on every rank.
 """
 from __future__ import annotations
 

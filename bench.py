@@ -53,6 +53,9 @@ def parse():
                     help="reference: the four active critics of the reference; ext: + body-slope (critics_warp.py:131-166), "
                          "roll and pitch critics (MppiParams.cw_slope_path / cw_roll / cw_pitch); auto: ext for C5, the "
                          "configuration BASELINE.json names with roll/pitch/slope critics, reference otherwise")
+    ap.add_argument("--dem-noise", type=float, default=0.0,
+                    help="diagnostic: add Gaussian cell-to-cell noise of this sigma (m) to the synthetic DEM (slopes then "
+                         "change by degrees per step and the STRICT tangent normalisation leaves its MUFU-free window)")
     ap.add_argument("--K", type=int, default=0, help="override the workload's samples per GPU (diagnostics)")
     ap.add_argument("--T", type=int, default=0, help="override the workload's horizon (diagnostics)")
     return ap.parse_args()
@@ -76,14 +79,19 @@ def kernel_counters(workload, math):
         return json.load(f).get(f"{workload}_{math}", {})
 
 
-def build_workload(name, K_override=0, T_override=0):
+def build_workload(name, K_override=0, T_override=0, dem_noise=0.0):
     from mppi_b200 import synthetic as syn
     w = syn.WORKLOADS[name]
+    if dem_noise > 0.0:
+        import dataclasses
+        w = dataclasses.replace(w, name=f"{w.name} [DEM + N(0, {dem_noise} m) per cell]")
     if K_override or T_override:
         import dataclasses
         w = dataclasses.replace(w, K=K_override or w.K, T=T_override or w.T,
                                 name=f"{w.name} [override K={K_override or w.K} T={T_override or w.T}]")
     dem = syn.crater_dem(w.grid_size, w.half_width).numpy()
+    if dem_noise > 0.0:
+        dem = dem + np.random.default_rng(2024).normal(0.0, dem_noise, dem.shape).astype(np.float32)
     cm = syn.rock_costmap(w.costmap_size, w.half_width)
     start, goal = syn.workload_start_goal(w)
     return w, dem, cm, start, goal
@@ -134,7 +142,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, dem, cm, start, goal = build_workload(args.workload, args.K, args.T)
+    w, dem, cm, start, goal = build_workload(args.workload, args.K, args.T, args.dem_noise)
     base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=max(5, args.warmup),
                                     critics=critic_weights(args))
     line = {
@@ -362,7 +370,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
-    w, dem_np, cm_np, start, goal = build_workload(args.workload, args.K, args.T)
+    w, dem_np, cm_np, start, goal = build_workload(args.workload, args.K, args.T, args.dem_noise)
     K, T = w.K, w.T                       # per-GPU samples
     K_total = K * n_gpus
     core = Core(K, T, device=local_rank, math=args.math,

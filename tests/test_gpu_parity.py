@@ -112,6 +112,20 @@ def test_rough_terrain_with_lethal_cells(oracle, variant):
 
 
 @both_variants
+def test_noisy_dem_takes_the_general_normalisation_path(oracle, variant):
+    """2 cm of cell-to-cell noise on the DEM: the slope under the rover changes by degrees between steps, so the
+    tangent projection leaves the +-2^-15 window of the MUFU-free shortcut on (nearly) every step, lanes diverge
+    between the two code paths, and the wheel slopes are large.  Still bit-identical to the oracle."""
+    n = np.full(80, 0.7, np.float32)
+    ref, got, d, sim = run_both(oracle, 2048, 80, "rough", nominal=(n, n), seed=11, variant=variant, philox=True)
+    check_strict(ref, got, d, sim)
+    # the scenario does what it says: |h . n| of consecutive steps is far outside the shortcut's window
+    hd, tr = ref.dump["heading"], ref.dump["traj"]
+    dz = np.abs(np.diff(hd[:, :, 2], axis=1))
+    assert np.median(dz) > 0.02 and np.max(np.abs(tr[:, -1, 0] - tr[:, 0, 0])) > 1.0
+
+
+@both_variants
 def test_near_goal_branches(oracle, variant):
     """dist < horizon -> path-follow near branch (sum of L1 distances); dist < 2 -> speed critic off."""
     n = np.full(50, 0.5, np.float32)

@@ -17,6 +17,10 @@ def terrain(name: str = "C1"):
         dem = syn.crater_dem(gs, hw, bumps=bumps).numpy()
         cm = syn.rock_costmap(cms, hw, n_rocks=60, seed=5)
         return dem, cm, hw
+    if name == "rough":                       # the C1 map with 2 cm of cell-to-cell noise: slopes change by several
+        dem, cm, hw = terrain("C1")           # degrees per step, as on a photogrammetric DEM
+        rng = np.random.default_rng(2024)
+        return (dem + rng.normal(0.0, 0.02, dem.shape).astype(np.float32)), cm, hw
     w = syn.WORKLOADS[name]
     dem = syn.crater_dem(w.grid_size, w.half_width).numpy()
     cm = syn.rock_costmap(w.costmap_size, w.half_width)

@@ -77,3 +77,24 @@ def test_synthetic_workloads_have_the_baseline_shapes():
     assert cm.shape == (64, 64) and cm.dtype == np.float32 and cm.max() == 1.0
     dem = synthetic.crater_dem(64, 6.4, bumps=[((0.0, 0.0), 1.0, 1.0)])
     assert tuple(dem.shape) == (64, 64)
+
+
+def test_bench_reference_arm_emits_the_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference path on the host cores) runs without a GPU and prints
+    ONE JSON line with the keys the measurement contract names."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "C1",
+                        "--steps", "3", "--warmup", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "MPPI sample-steps/s" and d["unit"] == "sample-steps/s"
+    assert d["higher_is_better"] is True and d["steps"] == 3 and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "C1" in d["config"]["workload"]

@@ -98,3 +98,17 @@ def test_near_unit_normalisation_shortcut_is_ieee_exact(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     bad_s, bad_q, n = (int(x) for x in r.stdout.split())
     assert r.returncode == 0 and bad_s == 0 and bad_q == 0 and n > 3e9
+
+
+def test_round_toward_zero_add_truncates_exactly(tmp_path):
+    """The pipelined kernel indexes its shared-memory DEM tile with one round-toward-zero FADD (+-2^23) instead of a
+    float->int conversion (csrc/mppi_device.cuh, tile_rel).  tests/arith_rz_trunc.c proves, for EVERY binary32 value in
+    [0, 32768] and its negative, that the integer in the mantissa equals the C truncation."""
+    import os
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "arith_rz_trunc.c")
+    exe = str(tmp_path / "arith_rz_trunc")
+    subprocess.run(["/usr/bin/gcc", "-O2", "-frounding-math", src, "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    bad, n = (int(x) for x in r.stdout.split())
+    assert r.returncode == 0 and bad == 0 and n > 1.19e9

@@ -10,7 +10,11 @@
 //            online softmax), writes the updated nominal, runs the (opt_k, opt_a) wheel filter and
 //            publishes (v*, w*).  In sample-sharded multi-GPU mode it writes the rank partial instead.
 //
-// Compiled twice: STRICT (-fmad=false ...) and FAST (-DMPPI_FLAVOR_FAST -use_fast_math).
+//            A block that can prove its partial will be scaled by exactly 0 (running minimum of the block
+//            minima, see partial_is_dead) publishes only its header.
+//
+// Compiled four times: STRICT (-fmad=false ...) and FAST (-DMPPI_FLAVOR_FAST -use_fast_math), each without and with
+// the optional critics (-DMPPI_XC), into the namespaces strict / fast / strict_xc / fast_xc.
 #include "mppi_kernels.cuh"
 #include "mppi_device.cuh"
 
@@ -30,8 +34,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 // slot: 0 entry, 1 set-up done, 2 rollout start, 3 rollout end, 4 all roles joined, 5 partial published,
 //       6 update finished (last block only), 7 SM id, 8 cost ready, 9 block min, 10 block sum + compaction,
-//       11 ticket taken, 12..15 last block: global min, ordered fold, nominal written, (v*, w*) written
-constexpr int kTraceSlots = 32;       // 16..31: SM-clock stamps inside the last block's update (cycles)
+//       11 ticket taken, 12..15 last block: global min, ordered fold, nominal written, (v*, w*) written,
+//       25 DEM tile landed (pipelined kernel)
+constexpr int kTraceSlots = 32;       // 16..24: SM-clock stamps inside the last block's update (cycles)
 __device__ __forceinline__ void trace_stamp(const FusedArgs& A, int slot)
 {
     if (A.trace != nullptr && blockIdx.y == 0) A.trace[(size_t)blockIdx.x * kTraceSlots + slot] = globaltimer_ns();
@@ -817,8 +822,10 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
 //   warp  5    obstacle  costmap gather + lethal penalty, near-goal path critic, last point
 // Warp w runs on SM sub-partition w % 4, so the chain and the wheel warps own a scheduler each and the light
 // roles share the other two.  Rings live in shared memory; chunks of kPipeChunk steps are handed over with
-// mbarriers (full/empty pairs), so the chain warp runs its dependent chain without ever issuing the other
-// roles' instructions.  Arithmetic per sample is unchanged (same device functions => same bits).
+// mbarriers (noise -> filter, and every "slot free" edge that a producer with slack waits on) and, for the two
+// conditions the CHAIN warp waits on, with release / acquire counters (see PipeSmem), so the chain warp runs its
+// dependent chain without issuing the other roles' instructions or paying an mbarrier wait.  Arithmetic per sample
+// is unchanged (same device functions => same bits).
 #ifndef MPPI_CHAIN_UNROLL
 #define MPPI_CHAIN_UNROLL 4         // unroll factor of the chain warp's per-chunk loop (A/B knob)
 #endif

@@ -43,7 +43,7 @@ enum { MPPI_MATH_STRICT = 0, MPPI_MATH_FAST = 1 };
 
 /* Fused-kernel variant.  Both compute the same bits; they differ in how a sample's step is mapped to warps.
  *  MONO: one thread per sample does everything (throughput regime, large K).
- *  PIPE: four specialised warps per 32 samples (noise/filter -> dependent chain -> wheel/slope and obstacle
+ *  PIPE: six specialised warps per 32 samples (2 x noise, filter -> dependent chain -> wheel/slope and obstacle
  *        critics) handing stages over through shared-memory rings (latency regime, K of a few thousand). */
 enum { MPPI_VARIANT_AUTO = 0, MPPI_VARIANT_MONO = 1, MPPI_VARIANT_PIPE = 2 };
 

@@ -119,6 +119,27 @@ def test_c_oracle_agrees_with_the_numpy_restatement_on_all_optional_critics(gold
         assert same_bits(c, r.dump["cost"])
 
 
+REENABLED = dict(cw_orient=1.0, cw_slope_path=50.5)      # the coefficients of the reference's commented lines :324, :326
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_oracle_total_cost_matches_the_reference_kernel_with_its_commented_lines_reenabled(gold, crit, oracle, name):
+    """tests/golden/make_golden_critics.py ran the reference's `_evaluate_trajectories_kernel` with the comment markers
+    of `costs[tid] += _path_orientation_critic(...)` (:324) and `costs[tid] += 50.5*_avoid_slope(...)` (:326) removed:
+    the oracle with cw_orient = 1, cw_slope_path = 50.5 reproduces those total costs, i.e. the two dormant terms sit
+    where the reference would add them."""
+    for sc, s, tag, st, g, ref in cases(gold, crit, name):
+        want = crit[f"{name}/step{s}/{tag}/reenabled_cost"]
+        p = oracle.make_params(K=sc["K"], T=sc["T"], lam=sc["lam"], proj=sc["proj"], math=oracle.MATH_LIBM,
+                               r_wheels=sc["radius"], horizon=sc["horizon"], input_model=sc["input_model"], **REENABLED)
+        r = oracle.mppi_step(p, sc["Z"], sc["hw"], sc["cm"], st, g("in/nominal1"), g("in/nominal2"), g("out/eps1"),
+                             g("out/eps2"), dump=["cost"])
+        assert rel(r.dump["cost"], want, 1.0) < RTOL, (name, s, tag)
+        assert r.argmin == int(np.argmin(want))
+        if tag == "own":          # and without the two weights it is the cost the unmodified kernel produced
+            assert not np.array_equal(want, g("out/costs"))
+
+
 def test_zero_weights_leave_the_reference_cost_untouched(gold, oracle):
     """Weight 0 means 'not evaluated, not added': an optional critic that would be NaN / inf cannot leak in."""
     name = "A3d"
@@ -164,6 +185,25 @@ def test_cuda_optional_critics_bit_exact_vs_oracle_and_within_tolerance_of_the_r
         assert rel(res["nominal1"], r.nominal1, 1e-2) < RTOL and rel(res["nominal2"], r.nominal2, 1e-2) < RTOL, key
         check_dormant(d["critics_ext"], ref, key)
         core.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_cuda_total_cost_matches_the_reference_kernel_with_its_commented_lines_reenabled(gold, crit, name):
+    """The CUDA path (STRICT, both fused kernels) against the same re-enabled reference kernel: costs within 1e-4,
+    argmin exact."""
+    from util import GpuCore
+    for variant in (1, 2):
+        for sc, s, tag, st, g, ref in cases(gold, crit, name):
+            want = crit[f"{name}/step{s}/{tag}/reenabled_cost"]
+            core = GpuCore(sc["K"], sc["T"], sc["Z"], sc["cm"], sc["hw"], math="strict", lambda_=sc["lam"],
+                           variant=variant, r_wheels=sc["radius"], horizon=sc["horizon"],
+                           input_model=sc["input_model"], **REENABLED)
+            core.set_nominal(g("in/nominal1"), g("in/nominal2"))
+            res = core.step(st, proj=sc["proj"], eps=(g("out/eps1"), g("out/eps2")))
+            assert rel(res["cost"], want, 1.0) < RTOL, (name, s, tag, variant)
+            assert res["argmin"] == int(np.argmin(want))
+            core.close()
 
 
 @pytest.mark.gpu

@@ -876,7 +876,14 @@ __device__ __forceinline__ int ld_acquire_cta(const int* p)
 __device__ __forceinline__ void warp_publish(int* counter, int v, int lane)
 {
     __syncwarp();
+#ifdef MPPI_AB_PUBLISH_RELAXED
+    // A/B knob, MEASUREMENT ONLY (make variant EXTRA=-DMPPI_AB_PUBLISH_RELAXED): a plain volatile store instead of
+    // st.release.cta (= MEMBAR.ALL.CTA + STS).  Not a release in the PTX memory model; it exists to measure what the
+    // three per-chunk MEMBARs of the sibling warps cost the chain warp.
+    if (lane == 0) *reinterpret_cast<volatile int*>(counter) = v;
+#else
     if (lane == 0) st_release_cta(counter, v);
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {

@@ -98,3 +98,19 @@ def test_bench_reference_arm_emits_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "C1" in d["config"]["workload"]
+
+
+def test_surface_reproduces_the_reference_surface_arrays():
+    """tests/golden/reference_mppi_steps.npz stores the DEM and the obstacle costmap the REFERENCE's `Surface`
+    (MPPI_isaac.py:259-378, run under the Warp shim by make_golden_warp.py) built for the golden scenarios; the facade's
+    `Surface` with the same arguments gives the same DEM bit for bit and the same costmap (cv2 on both sides)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_mppi_steps.npz"))
+    bumps = [((-1.5, 1.0), 1.4, 2.5), ((3.0, -1.0), 2.0, 3.0), ((0.5, 4.0), 0.9, 1.5), ((-4.0, -4.0), 1.2, 2.0)]
+    obstacles = [(1.0, 2.0, 0.6), (-2.0, -1.0, 0.8), (3.5, 3.0, 0.5), (0.0, -3.0, 0.7), (-3.0, 3.5, 0.4)]
+    s = Surface("manual", "", "manual", "", 160, 8.0, (0.0, 0.0), bumps, 0.3, obstacles)
+    assert np.array_equal(np.asarray(s.Z, np.float32), gold["A3d/Z"])
+    assert np.allclose(np.asarray(s.costmap, np.float32), gold["A3d/costmap"], rtol=2e-5, atol=1e-7)
+    assert (s.grid_size, s.costmap_size) == (160, int(gold["A3d/meta"][4]))
+    assert s.resolution == pytest.approx(float(gold["A3d/fmeta"][1])) and \
+        s.costmap_resolution == pytest.approx(float(gold["A3d/fmeta"][2]))

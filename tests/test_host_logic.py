@@ -114,3 +114,54 @@ def test_surface_reproduces_the_reference_surface_arrays():
     assert (s.grid_size, s.costmap_size) == (160, int(gold["A3d/meta"][4]))
     assert s.resolution == pytest.approx(float(gold["A3d/fmeta"][1])) and \
         s.costmap_resolution == pytest.approx(float(gold["A3d/fmeta"][2]))
+
+
+def test_facade_classes_agree_with_the_reference_classes_if_present():
+    """Live comparison (build container only): the reference's own `Surface`, `Robot` and `MPPI_Controller`
+    (MPPI_isaac.py, imported under the Warp shim -- constructing them needs no GPU) against the facade's, attribute
+    by attribute, after the same constructor calls and pose updates."""
+    import os
+    import sys
+    import types
+    ref_root = "/root/reference"
+    cfg = os.path.join(ref_root, "thesis_master/warp_implementation/config.yaml")
+    if not os.path.exists(cfg):
+        pytest.skip("reference tree not mounted")
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import warp_shim
+    saved = {k: sys.modules.get(k) for k in ("warp", "matplotlib", "matplotlib.pyplot")}
+    try:
+        sys.modules["warp"] = warp_shim
+        mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt
+        sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
+        sys.path.insert(0, ref_root)
+        import thesis_master.warp_implementation.MPPI_isaac as ref
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        if ref_root in sys.path:
+            sys.path.remove(ref_root)
+    bumps = [((-1.0, 0.5), 1.2, 2.0), ((2.0, -1.5), 1.8, 2.5)]
+    rocks = [(1.0, 1.0, 0.5), (-2.0, 0.5, 0.7)]
+    args = ("manual", "", "manual", "", 96, 4.8, (0.0, 0.0), bumps, 0.3, rocks)
+    a, b = ref.Surface(*args), Surface(*args)
+    for k in ("grid_size", "half_width", "resolution", "costmap_size", "costmap_resolution"):
+        assert getattr(a, k) == getattr(b, k), k
+    assert np.array_equal(np.asarray(a.Z, np.float32), np.asarray(b.Z, np.float32))
+    assert np.allclose(a.costmap, b.costmap, rtol=2e-5, atol=1e-7)
+    ra, rb = ref.Robot(0.3, -0.4, [3.0, 4.0, 0.0], cfg), Robot(0.3, -0.4, [3.0, 4.0, 0.0], cfg)
+    for r in (ra, rb):
+        r.update_position(0.5, -0.2, 0.1, np.array([0.0, 1.0, 0.0]))
+    for k in ("x", "y", "z", "radius", "left_wheel_speed", "right_wheel_speed", "lin_vel", "ang_vel"):
+        assert getattr(ra, k) == getattr(rb, k), k
+    assert np.array_equal(ra.heading_vector, rb.heading_vector)
+    ca, cb = ref.MPPI_Controller(a, ra, cfg, 3.0, 2.0, 2.2), MPPI_Controller(b, rb, cfg, 3.0, 2.0, 2.2)
+    for k in ("goal_x", "goal_y", "goal_orientation", "loop", "number_of_iterations", "dt", "number_of_trajectories",
+              "initial_linear_velocity", "initial_angular_velocity", "std_dev_u1", "std_dev_u2", "min_u1", "max_u1",
+              "min_u2", "max_u2", "v_min_linear", "v_max_linear", "v_min_angular", "v_max_angular", "temperature",
+              "horizon"):
+        assert getattr(ca, k) == getattr(cb, k), k

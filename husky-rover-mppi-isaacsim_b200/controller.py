@@ -357,13 +357,21 @@ class MPPI_Controller:
         capi.check(self._lib.mppi_export_trajectories(self._handle, C.byref(st), self._last_proj, noise, self.seed,
                                                       self._last_offset, 1, sample_stride, step_stride,
                                                       pts.data_ptr(), self._stream), "mppi_export_trajectories")
-        p = pts.reshape(-1, 3)
-        # float32 additions in the driver's order: (-y + block_x) + half_block
-        world = torch.stack([(-p[:, 1] + block_x_current) + half_block, (p[:, 0] + block_y_current) + half_block,
-                             p[:, 2]], dim=1)
-        costs = self.costs_wp.tensor[::sample_stride]
-        costs = (costs - costs.min()) / costs.max()
+        world = self.to_world_frame(pts.reshape(-1, 3), block_x_current, block_y_current, half_block)
+        costs = self.normalised_costs(self.costs_wp.tensor[::sample_stride])
         return world.cpu().numpy(), costs.repeat_interleave(nt).cpu().numpy()
+
+    @staticmethod
+    def to_world_frame(p: torch.Tensor, block_x_current: float, block_y_current: float, half_block: float):
+        """Block frame -> world frame of the driver's `transform_trajs` (visual_terrain_stack_full_terrain.py:257-259):
+        float32 additions in its order, (-y + block_x) + half_block and (x + block_y) + half_block; z unchanged."""
+        return torch.stack([(-p[:, 1] + block_x_current) + half_block, (p[:, 0] + block_y_current) + half_block,
+                            p[:, 2]], dim=1)
+
+    @staticmethod
+    def normalised_costs(costs: torch.Tensor):
+        """`(costs - min(costs)) / max(costs)` of the driver's visualiser feed (:524)."""
+        return (costs - costs.min()) / costs.max()
 
     def on_block_change(self, shift_x: float, shift_y: float, dem, rocks_data, origin):
         """The driver's terrain-block change (visual_terrain_stack_full_terrain.py:546-576) in one call: rebuild the

@@ -165,3 +165,39 @@ def test_facade_classes_agree_with_the_reference_classes_if_present():
               "min_u2", "max_u2", "v_min_linear", "v_max_linear", "v_min_angular", "v_max_angular", "temperature",
               "horizon"):
         assert getattr(ca, k) == getattr(cb, k), k
+
+
+def test_visualiser_transform_matches_the_drivers_transform_trajs_if_present():
+    """The driver's `transform_trajs` (visual_terrain_stack_full_terrain.py:252-261) cannot be imported (the file pulls
+    in Isaac Sim), but the function itself is plain NumPy: its source is cut out with `ast` and executed.  Its output
+    on a K x 100 x 3 array equals the facade's world-frame transform applied to the every-50th-sample /
+    every-10th-step subset, i.e. to what `mppi_export_trajectories` produces (that equality is a GPU test)."""
+    import ast
+    import os
+    import torch
+    path = "/root/reference/visual_terrain_stack_full_terrain.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    src = open(path).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "transform_trajs")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+
+    class FakeWarpArray:
+        def __init__(self, a):
+            self.a = a
+
+        def numpy(self):
+            return self.a
+
+    rng = np.random.default_rng(3)
+    K, T = 1000, 100
+    traj = rng.uniform(-20, 20, (K * T, 3)).astype(np.float32)
+    bx, by, hb = 123.25, -77.5, 20.0
+    want = ns["transform_trajs"](FakeWarpArray(traj), bx, by, hb, 0.0)
+    sub = torch.from_numpy(traj.reshape(K, T, 3)[::50, ::10].reshape(-1, 3).copy())
+    got = MPPI_Controller.to_world_frame(sub, bx, by, hb).numpy()
+    assert got.shape == want.shape == (20 * 10, 3) and np.array_equal(got, want)
+    c = torch.from_numpy(rng.uniform(100, 5000, K).astype(np.float32))[::50]
+    cn = c.numpy()
+    assert np.array_equal(MPPI_Controller.normalised_costs(c).numpy(), (cn - np.min(cn)) / np.max(cn))

@@ -50,10 +50,10 @@ def crater_dem(grid_size: int, half_width: float, bumps=None, seed: int = 57, de
     return Z.to(torch.float32)
 
 
-def rock_costmap(costmap_size: int, half_width: float, n_rocks: int = 750, seed: int = 99, r_robot: float = 0.3,
-                 power: float = 10.0) -> np.ndarray:
-    """float32 [costmap_size, costmap_size] obstacle costmap in [0, 1]."""
-    import cv2
+def rock_free_mask(costmap_size: int, half_width: float, n_rocks: int = 750, seed: int = 99,
+                   r_robot: float = 0.3) -> np.ndarray:
+    """uint8 [costmap_size, costmap_size]: 255 = free, 0 = inside a rock disc inflated by the robot radius + 0.2 m
+    (rocks: RandomState(99), centre U(-2/3 hw, 2/3 hw)^2, r in U(0, 0.4); MPPI_OO_current.py:723-725, :293)."""
     rng = np.random.RandomState(seed)
     span = half_width * 2.0 / 3.0
     xc = np.linspace(-half_width, half_width, costmap_size)
@@ -66,9 +66,22 @@ def rock_costmap(costmap_size: int, half_width: float, n_rocks: int = 750, seed:
         j0, j1 = max(0, int((oy - R + half_width) / res)), min(costmap_size, int((oy + R + half_width) / res) + 2)
         sub = (xc[None, i0:i1] - ox) ** 2 + (xc[j0:j1, None] - oy) ** 2 <= R * R
         free[j0:j1, i0:i1][sub] = 0
+    return free
+
+
+def costmap_from_free_mask(free: np.ndarray, power: float = 10.0) -> np.ndarray:
+    """The reference's offline recipe (create_costmap.py:14-28): L2 distance transform (5x5 mask) of the free space,
+    min-max normalised to [0, 1], cost = (1 - d)^power."""
+    import cv2
     dist = cv2.distanceTransform(free, cv2.DIST_L2, 5)
     dist = cv2.normalize(dist, None, 0, 1.0, cv2.NORM_MINMAX)
     return ((1.0 - dist) ** power).astype(np.float32)
+
+
+def rock_costmap(costmap_size: int, half_width: float, n_rocks: int = 750, seed: int = 99, r_robot: float = 0.3,
+                 power: float = 10.0) -> np.ndarray:
+    """float32 [costmap_size, costmap_size] obstacle costmap in [0, 1]."""
+    return costmap_from_free_mask(rock_free_mask(costmap_size, half_width, n_rocks, seed, r_robot), power)
 
 
 @dataclass

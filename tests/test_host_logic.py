@@ -201,3 +201,38 @@ def test_visualiser_transform_matches_the_drivers_transform_trajs_if_present():
     c = torch.from_numpy(rng.uniform(100, 5000, K).astype(np.float32))[::50]
     cn = c.numpy()
     assert np.array_equal(MPPI_Controller.normalised_costs(c).numpy(), (cn - np.min(cn)) / np.max(cn))
+
+
+def test_synthetic_costmap_recipe_is_the_reference_recipe_if_present():
+    """bench.py's obstacle costmaps come from `synthetic.costmap_from_free_mask`, which claims to be the reference's
+    offline recipe.  That recipe exists only as commented lines in create_costmap.py:14-28: here they are un-commented
+    in memory (np.load / np.save redirected to arrays) and executed on the same binary map -- identical costmap."""
+    import os
+    path = "/root/reference/thesis_master/warp_implementation/create_costmap.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    lines = open(path).read().split("\n")[13:28]
+    code = [l[2:] if l.startswith("# ") else l for l in lines if l.strip() and not l.startswith("# #")]
+    assert any("cv2.distanceTransform" in l for l in code) and any("**10" in l for l in code)
+    free = synthetic.rock_free_mask(256, 25.6, n_rocks=40, seed=5)
+    binary = (free == 0).astype(np.uint8)                       # the reference's map: 1 = obstacle, 0 = free space
+    saved = {}
+
+    class FakeNp:
+        def __getattr__(self, k):
+            return getattr(np, k)
+
+        @staticmethod
+        def load(name):
+            return binary
+
+        @staticmethod
+        def save(name, a):
+            saved[name] = a
+
+    import cv2
+    exec("\n".join(code), {"np": FakeNp(), "cv2": cv2})
+    assert list(saved) == ["costmap_750_transformed.npy"]
+    ours = synthetic.costmap_from_free_mask(free, 10.0)
+    assert np.array_equal(ours, saved["costmap_750_transformed.npy"].astype(np.float32))
+    assert np.array_equal(ours, synthetic.rock_costmap(256, 25.6, n_rocks=40, seed=5))

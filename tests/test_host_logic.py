@@ -236,3 +236,34 @@ def test_synthetic_costmap_recipe_is_the_reference_recipe_if_present():
     ours = synthetic.costmap_from_free_mask(free, 10.0)
     assert np.array_equal(ours, saved["costmap_750_transformed.npy"].astype(np.float32))
     assert np.array_equal(ours, synthetic.rock_costmap(256, 25.6, n_rocks=40, seed=5))
+
+
+def test_synthetic_scene_constants_are_the_references_if_present():
+    """The bench scene quotes the reference's own experiment constants: the nine craters, the start and
+    goal, and the rock generator (RandomState(99), 750 rocks within +-50 m of a 75 m map, r in U(0, 0.4), disc radius
+    r + r_robot + 0.2) are read back from the text of MPPI_OO_current.py and compared."""
+    import ast
+    import os
+    import re
+    path = "/root/reference/thesis_master/warp_implementation/MPPI_OO_current.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    text = open(path).read()
+    m = re.search(r"# bumps = \[\n((?:#\s+\(\(.*\n)+)# \]", text)
+    assert m
+    craters = ast.literal_eval("[" + "".join(l.lstrip("# ") for l in m.group(1).splitlines()) + "]")
+    assert craters == synthetic.NINE_CRATERS
+    nums = {k: float(re.search(r"#\s+#\s+%s = (-?[0-9.]+)" % k, text).group(1))
+            for k in ("x_start", "y_start", "x_goal", "y_goal")}
+    w = synthetic.WORKLOADS["C2"]
+    assert (nums["x_start"], nums["y_start"]) == w.start and (nums["x_goal"], nums["y_goal"]) == w.goal
+    assert "rng = np.random.RandomState(99)" in text and "for i in range(750):" in text
+    assert "rng.uniform(-50.0, 50.0), rng.uniform(-50.0, 50.0), rng.uniform(0.0, 0.4)" in text
+    assert "(r_obs + self.r_robot + 0.2) ** 2" in text
+    # the generator draws in the same order from the same stream: first rock of the 75 m map
+    rng = np.random.RandomState(99)
+    first = (rng.uniform(-50.0, 50.0), rng.uniform(-50.0, 50.0), rng.uniform(0.0, 0.4))
+    free = synthetic.rock_free_mask(750, 75.0, n_rocks=1)
+    xc = np.linspace(-75.0, 75.0, 750)
+    want = ((xc[None, :] - first[0]) ** 2 + (xc[:, None] - first[1]) ** 2) <= (first[2] + 0.3 + 0.2) ** 2
+    assert np.array_equal(free == 0, want)

@@ -116,10 +116,9 @@ def test_surface_reproduces_the_reference_surface_arrays():
         s.costmap_resolution == pytest.approx(float(gold["A3d/fmeta"][2]))
 
 
-def test_facade_classes_agree_with_the_reference_classes_if_present():
-    """Live comparison (build container only): the reference's own `Surface`, `Robot` and `MPPI_Controller`
-    (MPPI_isaac.py, imported under the Warp shim -- constructing them needs no GPU) against the facade's, attribute
-    by attribute, after the same constructor calls and pose updates."""
+def _reference_module():
+    """thesis_master/warp_implementation/MPPI_isaac.py imported under the Warp shim (no GPU needed to construct its
+    classes), or a skip when the reference tree is not mounted."""
     import os
     import sys
     import types
@@ -145,6 +144,14 @@ def test_facade_classes_agree_with_the_reference_classes_if_present():
                 sys.modules[k] = v
         if ref_root in sys.path:
             sys.path.remove(ref_root)
+    return ref, cfg
+
+
+def test_facade_classes_agree_with_the_reference_classes_if_present():
+    """Live comparison (build container only): the reference's own `Surface`, `Robot` and `MPPI_Controller`
+    (MPPI_isaac.py, imported under the Warp shim -- constructing them needs no GPU) against the facade's, attribute
+    by attribute, after the same constructor calls and pose updates."""
+    ref, cfg = _reference_module()
     bumps = [((-1.0, 0.5), 1.2, 2.0), ((2.0, -1.5), 1.8, 2.5)]
     rocks = [(1.0, 1.0, 0.5), (-2.0, 0.5, 0.7)]
     args = ("manual", "", "manual", "", 96, 4.8, (0.0, 0.0), bumps, 0.3, rocks)
@@ -267,3 +274,15 @@ def test_synthetic_scene_constants_are_the_references_if_present():
     xc = np.linspace(-75.0, 75.0, 750)
     want = ((xc[None, :] - first[0]) ** 2 + (xc[:, None] - first[1]) ** 2) <= (first[2] + 0.3 + 0.2) ** 2
     assert np.array_equal(free == 0, want)
+
+
+def test_synthetic_crater_dem_is_the_reference_surface_if_present():
+    """The C1 / C2 bench DEM (`synthetic.crater_dem(1500, 75.0)`: the nine craters) against the reference's own
+    `Surface.create_surface` (MPPI_isaac.py:300-322) for the same arguments.  The generator here adds each crater only
+    within +-6 widths of its centre (beyond that the Gaussians are < 2e-8 of the depth), hence 1e-6 instead of bits."""
+    ref, _ = _reference_module()
+    theirs = ref.Surface("manual", "", "", "", 1500, 75.0, (0.0, 0.0), synthetic.NINE_CRATERS, 0.3)
+    ours = synthetic.crater_dem(1500, 75.0).numpy()
+    assert ours.shape == np.asarray(theirs.Z).shape == (1500, 1500)
+    assert np.max(np.abs(ours - np.asarray(theirs.Z, np.float32))) < 1e-6
+    assert np.ptp(ours) > 4.0                                   # a real crater field (rims ~3.9 m, floors ~-1 m), not a plane

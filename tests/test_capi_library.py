@@ -118,3 +118,37 @@ def test_integration_md_binding_stub_matches_the_abi(capi):
         assert C.sizeof(mine) == C.sizeof(theirs), name
         norm = lambda n: "lam" if n == "lambda_" else n                                  # noqa: E731
         assert [(norm(n), t) for n, t in theirs._fields_] == [(n, t) for n, t in mine._fields_], name
+
+
+def test_default_literals_are_the_reference_source_literals_if_present(capi):
+    """`mppi_default_params` hard-codes the literals the reference scatters through its kernels and launch argument
+    lists.  With the reference tree mounted they are read back from the source text, line by line."""
+    base = "/root/reference/thesis_master/warp_implementation/"
+    if not os.path.exists(base + "critics_warp.py"):
+        pytest.skip("reference tree not mounted")
+    p = capi.default_params(1000, 100)
+    f32 = lambda v: C.c_float(v).value                                                    # noqa: E731
+
+    def line(path, n):
+        return open(base + path).read().split("\n")[n - 1]
+
+    def num(path, n, pattern):
+        m = re.search(pattern, line(path, n))
+        assert m, (path, n, line(path, n))
+        return f32(float(m.group(1)))
+
+    assert p.filt_k == num("MPPI_isaac.py", 548, r"^\s*([0-9.]+),") and p.filt_a == num("MPPI_isaac.py", 549, r"^\s*([0-9.]+)")
+    assert p.opt_k == num("MPPI_isaac.py", 688, r"^\s*([0-9.]+),") and p.opt_a == num("MPPI_isaac.py", 689, r"^\s*([0-9.]+)")
+    assert p.wheel_offset == num("projection_warp.py", 333, r"offset = ([0-9.]+)")
+    c = "critics_warp.py"
+    assert p.goal_angle_radius == num(c, 33, r"dist_to_goal < ([0-9.]+)")
+    assert p.pf_eps == num(c, 111, r"epsilon = ([0-9.e-]+)") and p.slope_eps == num(c, 188, r"epsilon = ([0-9.e-]+)")
+    assert p.pf_near_gain == num(c, 126, r"cost \+= ([0-9.]+) \*")
+    assert p.slope_gain == num(c, 209, r"\(1\.0 \+ ([0-9.]+)\*ratio_l\)")
+    assert p.lethal_thresh == num(c, 251, r"costmap_cost > ([0-9.]+)") and p.lethal_penalty == num(c, 252, r"\+= ([0-9.]+)")
+    assert p.near_goal_cut == num(c, 285, r"dist_to_goal < ([0-9.]+)")
+    assert p.speed_eps == num(c, 297, r"\+ ([0-9.]+)\)\s*$")
+    assert p.cw_path == num(c, 325, r"\+= ([0-9.]+)\*_path_follow_critic")
+    assert p.cw_slope == num(c, 327, r"\+= ([0-9.]+)\*_avoid_slope_wheels")
+    assert p.cw_speed == num(c, 328, r"\+= ([0-9.]+)\*_maximise_speed")
+    assert p.cw_obs == num(c, 329, r"\+= ([0-9.]+)\*_avoid_obstacle")

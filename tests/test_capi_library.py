@@ -152,3 +152,27 @@ def test_default_literals_are_the_reference_source_literals_if_present(capi):
     assert p.cw_slope == num(c, 327, r"\+= ([0-9.]+)\*_avoid_slope_wheels")
     assert p.cw_speed == num(c, 328, r"\+= ([0-9.]+)\*_maximise_speed")
     assert p.cw_obs == num(c, 329, r"\+= ([0-9.]+)\*_avoid_obstacle")
+
+
+def test_ctypes_mirrors_follow_the_header_field_by_field(capi):
+    """Field names, order and scalar types of every structure in include/mppi_b200.h against the ctypes mirrors of
+    capi.py (sizes alone would not notice two swapped floats)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "mppi_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    ctype = {"int32_t": C.c_int32, "float": C.c_float, "uint32_t": C.c_uint32}
+    for name in ("MppiParams", "MppiTerrain", "MppiState", "MppiOutputs", "MppiDebugDump"):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            m = re.match(r"(?:const )?(\w+) (.*)", decl)
+            base, rest = m.group(1), m.group(2)
+            for item in rest.split(","):
+                item = item.strip()
+                ptr = item.startswith("*")
+                fields.append((item.lstrip("*").strip(), C.c_void_p if ptr else ctype[base]))
+        mirror = [("lambda" if n == "lam" else n, t) for n, t in getattr(capi, name)._fields_]
+        assert mirror == fields, name

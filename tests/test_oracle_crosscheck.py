@@ -175,3 +175,29 @@ def test_velocity_space_input_model_c_vs_numpy(oracle):
     np.testing.assert_allclose(c.dump["cost"], n["cost"], rtol=2e-5)
     np.testing.assert_allclose(c.nominal1, n["nominal1"], rtol=1e-5, atol=1e-6)
     assert np.array_equal(c.opt_v, c.nominal1) and np.array_equal(c.opt_w, c.nominal2)
+
+
+def test_oracle_ctypes_mirrors_follow_the_oracle_header():
+    """oracle/oracle_c.py mirrors the structures of oracle/mppi_oracle.h by hand: field names, order and types are
+    compared here, so that a new field cannot silently shift the checker's arguments."""
+    import ctypes as C
+    import os
+    import re
+    from oracle import oracle_c
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "oracle", "mppi_oracle.h")).read(), flags=re.S)
+    ctype = {"int32_t": C.c_int32, "float": C.c_float, "double": C.c_double}
+    rename = {"lambda": "lam"}
+    for name in ("OrParams", "OrTerrain", "OrState", "OrDump", "OrOut"):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            m = re.match(r"(?:const )?(\w+) (.*)", decl)
+            for item in m.group(2).split(","):
+                item = item.strip()
+                n = item.lstrip("*").strip()
+                fields.append((rename.get(n, n), C.c_void_p if item.startswith("*") else ctype[m.group(1)]))
+        assert list(getattr(oracle_c, name)._fields_) == fields, name

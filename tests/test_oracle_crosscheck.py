@@ -201,3 +201,23 @@ def test_oracle_ctypes_mirrors_follow_the_oracle_header():
                 n = item.lstrip("*").strip()
                 fields.append((rename.get(n, n), C.c_void_p if item.startswith("*") else ctype[m.group(1)]))
         assert list(getattr(oracle_c, name)._fields_) == fields, name
+
+
+def test_oracle_result_does_not_depend_on_its_thread_count(oracle):
+    """The CPU baseline runs the oracle on all host cores (bench.py); its outputs must be the same bits as the
+    single-threaded run the parity tests use (static partition of the samples, sequential reductions)."""
+    from util import default_state, normals, terrain
+    dem, cm, hw = terrain("small")
+    K, T = 333, 40
+    st = default_state(x=-5.0, y=-4.0, hx=0.6, hy=0.8, goal_x=8.0, goal_y=9.0)
+    e1, e2 = normals(K, T, 9)
+    n = np.full(T, 0.4, np.float32)
+    p = oracle.make_params(K=K, T=T, lam=40.0, cw_pitch=250.0)
+    runs = [oracle.mppi_step(p, dem, hw, cm, st, n, n, e1, e2, dump=["cost", "traj", "critics_ext"], nthreads=t)
+            for t in (1, 3, 16)]
+    for r in runs[1:]:
+        assert np.array_equal(r.dump["cost"], runs[0].dump["cost"]) and np.array_equal(r.dump["traj"], runs[0].dump["traj"])
+        assert np.array_equal(r.dump["critics_ext"], runs[0].dump["critics_ext"])
+        assert np.array_equal(r.nominal1, runs[0].nominal1) and np.array_equal(r.opt_w, runs[0].opt_w)
+        assert (r.argmin, r.min_cost, r.weights_sum, r.oob_clamps) == (runs[0].argmin, runs[0].min_cost,
+                                                                      runs[0].weights_sum, runs[0].oob_clamps)

@@ -286,3 +286,27 @@ def test_synthetic_crater_dem_is_the_reference_surface_if_present():
     assert ours.shape == np.asarray(theirs.Z).shape == (1500, 1500)
     assert np.max(np.abs(ours - np.asarray(theirs.Z, np.float32))) < 1e-6
     assert np.ptp(ours) > 4.0                                   # a real crater field (rims ~3.9 m, floors ~-1 m), not a plane
+
+
+def test_committed_bench_line_carries_the_measurement_contract():
+    """The last C2 line measured on a B200 this round (profiles/r1_bench/) has every key the measurement contract
+    names, with consistent values -- a schema check of what bench.py's GPU arm emits (that arm cannot run here)."""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = sorted(glob.glob(os.path.join(root, "profiles", "r1_bench", "r1o_bench_c2_strict.json")))[-1]
+    d = json.loads([l for l in open(path) if l.startswith("{")][0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert "C2" in d["config"]["workload"] and "model" not in d["config"] and d["warmup"] >= 3
+    assert d["gpu_launches"] == d["steps"]                                   # ONE fused launch per control iteration
+    assert abs(d["value"] - 4096 * 100 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 48 and d["e2e"]["d2h_bytes_per_step"] == 8 and d["e2e"]["value"] < d["value"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["ms_per_step"] * 1e3 < 100.0                                    # BASELINE target: C2 under 100 us

@@ -2,20 +2,31 @@
 """bench.py -- MPPI hot-path benchmark (one JSON line on stdout, contract in the task statement).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1..C5] [--math strict|fast] [--critics auto|reference|ext]
-                  [--exchange p2p|nccl] [--variant auto|mono|pipe]
+                  [--exchange p2p|nccl] [--variant auto|mono|pipe] [--no-extras]
   python bench.py --impl reference ...        # CPU port of the reference path on the host cores
   tools/ab.sh <other libmppi_b200.so> [bench args]   # same-node A/B of two builds (MPPI_B200_LIB selects the library)
 
 A "step" is one full control iteration (sample -> wheel filter -> rollout on the DEM -> critics -> softmax
 update -> (v*, w*)) of ONE fused kernel launch over synthetic terrain of the BASELINE.json shape.
-N = 1 runs BASELINE config 2 (K = 4096, T = 100, 1500^2 DEM, 750^2 costmap).  N > 1 keeps that per-GPU
-workload (weak scaling): one logical controller with N x 4096 samples, sample-sharded, whose only exchange is the
-816-byte softmax partial per block / rank: stored into every rank's buffer over NVLink peer memory inside the fused
-launch (default), or one NCCL all-gather + combine kernel (--exchange nccl); the same deterministic fold on every rank.
+
+TOP-LEVEL LINE.  N = 1 runs BASELINE config 2 (K = 4096, T = 100, 1500^2 DEM, 750^2 costmap).  N > 1 keeps that
+per-GPU workload (weak scaling): one logical controller with N x 4096 samples, sample-sharded, whose only exchange is
+the softmax partial per block: flag-in-data lines stored into every rank's buffer over NVLink peer memory inside the
+fused launch (default), or one NCCL all-gather + combine kernel (--exchange nccl).
+
+SAME RUN, SAME LINE (skipped with --no-extras or a non-default --workload):
+  "sharded_check"  one step of the sharded controller with both transports against the UNSHARDED controller over
+                   K_total samples on one GPU (same block shape): bitwise for the fused exchange, relative for NCCL,
+                   argmin equal, all ranks identical; at two temperatures (0.3: argmin-like, 2000: every sample carries
+                   weight).  A mismatch makes the process exit non-zero.
+  "c3"             BASELINE config 3, K = 262144 samples, T = 100, 2048^2 DEM: "weak" (262144 samples per GPU) and
+                   "strong" (262144 samples in total) sample sharding, each with its own equality check.
+  "c4"             BASELINE config 4, rover-sharded batch (512 rovers x K = 1024 x T = 64 per GPU), no communication.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -29,8 +40,10 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_SAMPLE_STEP = 230.0      # SURVEY.md Appendix B (3-D skid-steer path)
 GATHER_BYTES_PER_SAMPLE_STEP = 28.0   # 7 gathered fp32 words (4 DEM corners + 2 wheel cells + 1 costmap cell)
+GATHER_SECTORS_PER_SAMPLE_STEP = 5.0  # 2 corner rows + 2 wheel cells + 1 costmap cell, 32-byte sectors (worst case)
 STATE_BYTES = 48                  # sizeof(MppiState): the per-step host input
 CMD_BYTES = 8                     # (v*[0], w*[0]) read back per step
+PIPE_MAX_SAMPLES = 148 * 32 * 2   # pick_launch (mppi_capi.cu): pipelined kernel up to this many samples in flight
 
 
 def parse():
@@ -47,8 +60,12 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the closed-loop (run()) measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip sharded_check and the c3 / c4 sub-objects")
+    ap.add_argument("--latency-steps", type=int, default=1000,
+                    help="back-to-back iterations of the latency leg (p50 / p99 do not depend on --steps)")
+    ap.add_argument("--extras-steps", type=int, default=30, help="timed iterations of each c3 / c4 sub-measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--rovers", type=int, default=512, help="C4 only: rovers per GPU (4096 rovers / 8 GPUs)")
+    ap.add_argument("--rovers", type=int, default=512, help="C4: rovers per GPU (4096 rovers / 8 GPUs)")
     ap.add_argument("--critics", choices=["auto", "reference", "ext"], default="auto",
                     help="reference: the four active critics of the reference; ext: + body-slope (critics_warp.py:131-166), "
                          "roll and pitch critics (MppiParams.cw_slope_path / cw_roll / cw_pitch); auto: ext for C5, the "
@@ -56,6 +73,9 @@ def parse():
     ap.add_argument("--dem-noise", type=float, default=0.0,
                     help="diagnostic: add Gaussian cell-to-cell noise of this sigma (m) to the synthetic DEM (slopes then "
                          "change by degrees per step and the STRICT tangent normalisation leaves its MUFU-free window)")
+    ap.add_argument("--start", default="bench", choices=["bench", "rocks"],
+                    help="bench: the reference's start (-60.57, -60.23), flat ground outside the rock field; rocks: a start "
+                         "inside the rock field on a crater wall (the C2rock golden scenario)")
     ap.add_argument("--K", type=int, default=0, help="override the workload's samples per GPU (diagnostics)")
     ap.add_argument("--T", type=int, default=0, help="override the workload's horizon (diagnostics)")
     return ap.parse_args()
@@ -70,23 +90,51 @@ def peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
 
 
-def kernel_counters(workload, math):
-    """Per-launch counters of the dominant kernel taken from the committed ncu capture (profiles/), if any."""
+def live_peaks(device):
+    """FP32 FMA throughput and L2 gather rate measured NOW on this device (csrc/peaks.cu): the roofline denominators
+    MEASURED_PEAKS.json has no figure for."""
+    from mppi_b200 import capi
+    a, b, c = C.c_float(), C.c_float(), C.c_float()
+    if not hasattr(capi.lib(), "mppi_measure_peaks"):        # A/B against an older library (MPPI_B200_LIB)
+        clk = peaks()["sm_max_mhz"]
+        return dict(fp32_tflops=148 * 128 * 2 * clk * 1e6 / 1e12, l2_gather_gsectors=float("nan"), l2_gather_gbs=float("nan"),
+                    how="NOT measured (library without mppi_measure_peaks): 148 SM x 128 lanes x 2 x sm_max_mhz")
+    capi.check(capi.lib().mppi_measure_peaks(device, 8 << 20, C.byref(a), C.byref(b), C.byref(c)), "mppi_measure_peaks")
+    return dict(fp32_tflops=float(a.value), l2_gather_gsectors=float(b.value), l2_gather_gbs=float(c.value),
+                how="csrc/peaks.cu on this device just before the timed region: 8 independent FFMA chains per thread, "
+                    "8 x 256 threads per SM; random 4-byte .cg gathers in an 8 MiB L2-resident window")
+
+
+def kernel_counters(workload, math, K, T, variant):
+    """Per-launch counters of the dominant kernel from the committed ncu capture (profiles/kernel_counters.json).
+    They describe ONE configuration: used as they are only when K, T and the kernel match; scaled by K T and marked
+    extrapolated for another size of the same kernel; absent otherwise."""
     p = os.path.join(ROOT, "profiles", "kernel_counters.json")
     if not os.path.exists(p):
         return {}
     with open(p) as f:
-        return json.load(f).get(f"{workload}_{math}", {})
+        c = json.load(f).get(f"{workload}_{math}")
+    if not c or c.get("variant", variant) != variant:
+        return {}
+    K0, T0 = c.get("K"), c.get("T")
+    if K0 is None or T0 is None:
+        return {}
+    if (K0, T0) == (K, T):
+        return dict(c, extrapolated=False)
+    s = (K * T) / float(K0 * T0)
+    return dict(c, warp_inst_per_launch=c["warp_inst_per_launch"] * s, dram_bytes_per_launch=None, extrapolated=True)
 
 
-def build_workload(name, K_override=0, T_override=0, dem_noise=0.0):
+ROCK_START = dict(start=(-16.37, -31.73), heading=(0.6, -0.8, 0.0), goal=(20.0, -48.0))    # the C1rock / C2rock golden scene
+
+
+def build_workload(name, K_override=0, T_override=0, dem_noise=0.0, start_kind="bench"):
     from mppi_b200 import synthetic as syn
+    import dataclasses
     w = syn.WORKLOADS[name]
     if dem_noise > 0.0:
-        import dataclasses
         w = dataclasses.replace(w, name=f"{w.name} [DEM + N(0, {dem_noise} m) per cell]")
     if K_override or T_override:
-        import dataclasses
         w = dataclasses.replace(w, K=K_override or w.K, T=T_override or w.T,
                                 name=f"{w.name} [override K={K_override or w.K} T={T_override or w.T}]")
     dem = syn.crater_dem(w.grid_size, w.half_width).numpy()
@@ -94,7 +142,14 @@ def build_workload(name, K_override=0, T_override=0, dem_noise=0.0):
         dem = dem + np.random.default_rng(2024).normal(0.0, dem_noise, dem.shape).astype(np.float32)
     cm = syn.rock_costmap(w.costmap_size, w.half_width)
     start, goal = syn.workload_start_goal(w)
-    return w, dem, cm, start, goal
+    heading = (1.0, 0.0, 0.0)
+    if start_kind == "rocks":
+        s = w.scale
+        start = (ROCK_START["start"][0] * s, ROCK_START["start"][1] * s)
+        goal = (ROCK_START["goal"][0] * s, ROCK_START["goal"][1] * s)
+        heading = ROCK_START["heading"]
+        w = dataclasses.replace(w, name=f"{w.name} [start inside the rock field]")
+    return w, dem, cm, start, goal, heading
 
 
 EXT_CRITICS = dict(cw_slope_path=50.5, cw_roll=400.0, cw_pitch=250.0)
@@ -107,7 +162,7 @@ def critic_weights(args):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(w, dem, cm, start, goal, seconds, steps=None, warmup=0, K=None, critics=None):
+def cpu_reference_run(w, dem, cm, start, goal, seconds, steps=None, warmup=0, K=None, critics=None, heading=(1.0, 0.0, 0.0)):
     """Times the C port of the reference path (oracle/mppi_oracle.c, libm math) on all host cores."""
     from oracle import oracle_c as oc
     oc.build()
@@ -115,7 +170,8 @@ def cpu_reference_run(w, dem, cm, start, goal, seconds, steps=None, warmup=0, K=
     T = w.T
     threads = oc.num_threads()
     p = oc.make_params(K=K, T=T, math=oc.MATH_LIBM, **(critics or {}))
-    st = dict(x=start[0], y=start[1], hx=1.0, hy=0.0, hz=0.0, wheel_l=0.0, wheel_r=0.0, sigma1=0.25, sigma2=0.25,
+    hn = np.asarray(heading, np.float64) / np.linalg.norm(heading)
+    st = dict(x=start[0], y=start[1], hx=hn[0], hy=hn[1], hz=hn[2], wheel_l=0.0, wheel_r=0.0, sigma1=0.25, sigma2=0.25,
               goal_x=goal[0], goal_y=goal[1], goal_theta=2.2)
     rng = np.random.default_rng(0)
     e1 = rng.standard_normal((K, T)).astype(np.float32)
@@ -138,22 +194,58 @@ def cpu_reference_run(w, dem, cm, start, goal, seconds, steps=None, warmup=0, K=
                 ms_per_step=float(times.mean() * 1e3), p50_ms=float(np.median(times) * 1e3)), times
 
 
+def cpu_reference_script_run(w, samples=32):
+    """BASELINE.md baseline B0: the reference's OWN CPU projection function `generate_trajectory_25D`
+    (thesis_master/python_mppi_projection/displacement_on_surface.py:317-369, extracted as written into oracle/_ref/ by
+    oracle/make_ref.py) timed on this machine, one trajectory at a time on one core, as the script runs it.  Rollout
+    only: the script has no wheels, critics or update, so this is a floor of the reference's CPU cost of an iteration."""
+    from oracle import make_ref
+    ns = make_ref.load()
+    if ns is None:
+        return {"unavailable": "oracle/_ref/displacement_functions.py not built (python oracle/make_ref.py in the build container)"}
+    from mppi_b200 import synthetic as syn
+    T = w.T
+    X, Y, Z = ns["create_surface"](w.grid_size, w.half_width, syn.NINE_CRATERS[:3])
+    res = 2 * w.half_width / w.grid_size
+    rng = np.random.default_rng(0)
+    times = []
+    for k in range(samples + 2):
+        v = rng.uniform(0.2, 2.0, T)
+        om = rng.uniform(-1.0, 1.0, T)
+        t0 = time.perf_counter()
+        ns["generate_trajectory_25D"](-10.0, -10.0, np.array([1.0, 0.0, 0.0]), v, om, 0.045, T, res, X, Y, Z)
+        if k >= 2:
+            times.append(time.perf_counter() - t0)
+    per = float(np.median(times)) / T
+    return {"value": 1.0 / per, "unit": "sample-steps/s", "cores": 1, "kind": "reference",
+            "us_per_sample_step": per * 1e6, "iteration_rollout_only_s": per * w.K * T,
+            "sample": f"{samples} calls of the reference's generate_trajectory_25D (displacement_on_surface.py:317-369 as "
+                      f"written, via oracle/_ref), T={T}, one core, rollout only (no wheels / critics / update)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, dem, cm, start, goal = build_workload(args.workload, args.K, args.T, args.dem_noise)
-    base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=max(5, args.warmup),
-                                    critics=critic_weights(args))
+    w, dem, cm, start, goal, heading = build_workload(args.workload, args.K, args.T, args.dem_noise, args.start)
+    # like for like with the repo arm at N GPUs: ONE logical controller over K_total = N x K samples (C4: N x rovers)
+    n = max(1, args.gpus)
+    if args.workload == "C4":
+        K_total, units_note = w.K, f"{args.rovers * n} rovers of K={w.K} T={w.T}: ONE rover iteration timed per step, value scaled by 1"
+    else:
+        K_total, units_note = w.K * n, f"K_total = {n} x {w.K}"
+    base, times = cpu_reference_run(w, dem, cm, start, goal, seconds=None, steps=args.steps, warmup=max(3, min(args.warmup, 5)),
+                                    K=K_total, critics=critic_weights(args), heading=heading)
     line = {
         "impl": "reference", "metric": "MPPI sample-steps/s", "value": base["value"], "unit": "sample-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "K": w.K, "T": w.T, "dem": f"{w.grid_size}x{w.grid_size} f32",
-                   "costmap": f"{w.costmap_size}x{w.costmap_size} f32",
+        "config": {"workload": w.name, "K_per_gpu": w.K, "K_total": K_total, "T": w.T,
+                   "dem": f"{w.grid_size}x{w.grid_size} f32", "costmap": f"{w.costmap_size}x{w.costmap_size} f32",
                    "critics": "reference 4 + body-slope, roll, pitch" if critic_weights(args) else "reference 4",
+                   "problem": units_note,
                    "note": "the reference's GPU path needs NVIDIA Warp (absent, no network); this arm is the C port "
-                           "of its kernels on the host cores"},
+                           "of its kernels on the host cores, on the same K_total as the repo arm at this --gpus"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "latency_us": {"p50": float(np.median(times) * 1e6), "p99": float(np.percentile(times, 99) * 1e6)},
@@ -208,25 +300,206 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------ multi-rover batch (C4)
-def run_rover_batch(args):
-    """BASELINE config 4: independent controllers sharded by rover, no communication.  Each GPU runs
-    `--rovers` rovers (default 512 = 4096 / 8) x K = 1024 x T = 64 in ONE launch (grid.y = rover); every rover has
-    its own DEM / costmap memory, pose, goal, nominal and Philox stream."""
+# ------------------------------------------------------------------------------------------ shared GPU plumbing
+class Ctx:
+    """Process-wide state of the GPU arm: rank / world, device, the L2 flush buffer."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+        self.do_flush = not args.no_flush
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_equal(self, arr: np.ndarray) -> bool:
+        """True when every rank holds bitwise the same float32 array."""
+        if self.world == 1:
+            return True
+        mine = self.torch.from_numpy(np.ascontiguousarray(arr, np.float32).view(np.int32).copy()).to(self.dev)
+        every = self.torch.empty((self.world, mine.numel()), dtype=self.torch.int32, device=self.dev)
+        self.dist.all_gather_into_tensor(every, mine)
+        return bool((every == every[0]).all().item())
+
+    def timed_loop(self, fn, n, first, flush):
+        """n launches of fn(i), each bracketed by CUDA events on the current stream; returns ms per launch."""
+        torch = self.torch
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for i in range(n):
+            if flush:
+                self.flush_buf.fill_(i & 0xff)
+            evs[i][0].record()
+            fn(first + i)
+            evs[i][1].record()
+        torch.cuda.synchronize(self.dev)
+        return np.array([a.elapsed_time(b) for a, b in evs], dtype=np.float64)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def variant_id(name):
+    from mppi_b200 import capi
+    return {"auto": capi.VARIANT_AUTO, "mono": capi.VARIANT_MONO, "pipe": capi.VARIANT_PIPE}[name]
+
+
+def make_sharded(ctx, K_local, T, dem, cm, hw, transport, math="strict", variant="auto", **overrides):
+    """(core, stepper-or-None) of one logical controller with world x K_local samples on this rank's device."""
+    from mppi_b200.core import Core
+    from mppi_b200.sharding import SampleShardedStepper
+    core = Core(K_local, T, device=ctx.local_rank, math=math, variant=variant_id(variant), **overrides)
+    core.set_terrain(dem, hw, cm)
+    stepper = SampleShardedStepper(core, K_local * ctx.world, transport=transport) if ctx.world > 1 else None
+    return core, stepper
+
+
+def read_result(core):
+    ctx_sync = core.optimal_u1.device
     import torch
-    import torch.distributed as dist
+    torch.cuda.synchronize(ctx_sync)
+    return dict(u1=core.optimal_u1[0].cpu().numpy().copy(), u2=core.optimal_u2[0].cpu().numpy().copy(),
+                v=core.optimal_v[0].cpu().numpy().copy(), **core.read_stats())
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3)))
+
+
+def equality_check(ctx, K_local, T, dem, cm, hw, state, lambdas=(0.3, 2000.0), transports=("p2p", "nccl"),
+                   same_block_shape=True, math="strict"):
+    """One step of the sample-sharded controller (every transport) against the UNSHARDED controller over
+    K_total = world x K_local samples on this GPU, from a warm nominal, per temperature.  `same_block_shape`: the
+    unsharded launch is forced onto the kernel the shards use (the pipelined one, 32 samples per block), which is what
+    makes the fused exchange BITWISE comparable; otherwise the comparison is relative."""
+    from mppi_b200 import capi
+    from mppi_b200.core import Core
+    K_total = K_local * ctx.world
+    nom = np.full(T, 0.35, np.float32)
+    pipe_shards = K_local <= PIPE_MAX_SAMPLES
+    out = {"K_total": K_total, "transports": list(transports), "lambdas": list(lambdas), "passed": True, "cases": []}
+    for lam in lambdas:
+        full = Core(K_total, T, device=ctx.local_rank, math=math, lambda_=lam,
+                    variant=capi.VARIANT_PIPE if (same_block_shape and pipe_shards) else capi.VARIANT_AUTO)
+        full.set_terrain(dem, hw, cm)
+        full.set_nominal(nom, nom)
+        full.step(state, capi.PROJ_3D, None, 5, 11)
+        ref = read_result(full)
+        full.close()
+        case = {"lambda": lam, "ess_unsharded": ref["ess"], "argmin_unsharded": ref["argmin"]}
+        for tr in transports:
+            if ctx.world == 1 and tr == "nccl":
+                continue
+            core, stepper = make_sharded(ctx, K_local, T, dem, cm, hw, tr, math=math, lambda_=lam)
+            got = None
+            for it in range(3):                      # three iterations: both parities of the exchange buffers
+                core.set_nominal(nom, nom)
+                if stepper is None:
+                    core.step(state, capi.PROJ_3D, None, 5, 11)
+                else:
+                    stepper.step(state, capi.PROJ_3D, 5, 11)
+                got = read_result(core)
+            bitwise = bool(np.array_equal(got["u1"], ref["u1"]) and np.array_equal(got["u2"], ref["u2"])
+                           and np.array_equal(got["v"], ref["v"]))
+            r = max(rel_err(got["u1"], ref["u1"]), rel_err(got["u2"], ref["u2"]))
+            same = ctx.all_equal(np.concatenate([got["u1"], got["u2"], got["v"]]))
+            ok = (got["argmin"] == ref["argmin"]) and (got["min_cost"] == ref["min_cost"]) and same and r < 1e-5
+            if tr == "p2p" and same_block_shape and pipe_shards:
+                ok = ok and bitwise
+            case[tr] = {"bitwise": bitwise, "rel": r, "argmin_equal": got["argmin"] == ref["argmin"],
+                        "ranks_identical": same, "ok": bool(ok)}
+            out["passed"] = out["passed"] and bool(ok)
+            core.close()
+        out["cases"].append(case)
+    # every rank must agree on the verdict
+    out["passed"] = ctx.max_over_ranks(0.0 if out["passed"] else 1.0) == 0.0
+    # the summary keys the round-1 verdict asked for
+    first = out["cases"][0]
+    out["p2p_bitwise"] = all(c.get("p2p", {}).get("bitwise", True) for c in out["cases"])
+    out["nccl_rel"] = max([c["nccl"]["rel"] for c in out["cases"] if "nccl" in c], default=None)
+    out["argmin_equal"] = all(v["argmin_equal"] for c in out["cases"] for k, v in c.items() if isinstance(v, dict))
+    del first
+    return out
+
+
+def measure_sample_sharded(ctx, core, stepper, state, K_local, T, steps, warmup, seed=42):
+    """Device-timed sample-sharded iterations: `steps` launches, CUDA events, barrier + synchronise on both sides,
+    max over ranks.  Returns (ms_per_step, per-step ms of this rank, value in sample-steps/s)."""
+    from mppi_b200 import capi
+
+    def one(i):
+        if stepper is None:
+            core.step(state, capi.PROJ_3D, None, seed, i)
+        else:
+            stepper.step(state, capi.PROJ_3D, seed, i)
+
+    ctx.timed_loop(one, max(3, warmup), 0, ctx.do_flush)
+    ctx.barrier()
+    per = ctx.timed_loop(one, steps, 1000, ctx.do_flush)
+    ctx.barrier()
+    ms = ctx.max_over_ranks(float(per.sum())) / steps
+    return ms, per, K_local * ctx.world * T / (ms * 1e-3), one
+
+
+def run_c3(ctx, args):
+    """BASELINE config 3 inside the default run: weak (K = 262144 per GPU) and strong (K = 262144 in total)."""
+    import torch
+    from mppi_b200 import synthetic as syn
+    from mppi_b200.core import make_state
+    w = syn.WORKLOADS["C3"]
+    dem = syn.crater_dem(w.grid_size, w.half_width, device=ctx.dev).contiguous()
+    cm = torch.from_numpy(syn.rock_costmap(w.costmap_size, w.half_width)).to(ctx.dev)
+    start, goal = syn.workload_start_goal(w)
+    state = make_state(start[0], start[1], (1.0, 0.0, 0.0), goal_x=goal[0], goal_y=goal[1])
+    out = {"workload": w.name, "T": w.T, "dem": f"{w.grid_size}x{w.grid_size} f32", "math": args.math,
+           "exchange": args.exchange, "steps": args.extras_steps}
+    for mode, K_local in (("weak", w.K), ("strong", w.K // ctx.world)):
+        if mode == "strong" and ctx.world == 1:
+            out["strong"] = dict(out["weak"], note="N = 1: identical to weak")
+            continue
+        core, stepper = make_sharded(ctx, K_local, w.T, dem, cm, w.half_width, args.exchange, math=args.math)
+        ms, per, value, _ = measure_sample_sharded(ctx, core, stepper, state, K_local, w.T, args.extras_steps, 5)
+        core.close()
+        chk = equality_check(ctx, K_local, w.T, dem, cm, w.half_width, state, lambdas=(0.3,), transports=(args.exchange,),
+                             same_block_shape=False, math=args.math)
+        out[mode] = {"K_per_gpu": K_local, "K_total": K_local * ctx.world, "ms_per_step": ms, "value": value,
+                     "unit": "sample-steps/s", "p50_us": float(np.median(per) * 1e3),
+                     "check": {"passed": chk["passed"], "rel": chk["cases"][0][args.exchange]["rel"],
+                               "argmin_equal": chk["argmin_equal"],
+                               "ranks_identical": chk["cases"][0][args.exchange]["ranks_identical"]}}
+    return out
+
+
+def run_c4(ctx, args, K=0, T=0):
+    """BASELINE config 4: independent controllers sharded by rover, no communication.  Each GPU runs `--rovers`
+    rovers (default 512 = 4096 / 8) x K = 1024 x T = 64 in ONE launch (grid.y = rover); every rover has its own DEM /
+    costmap memory, pose, goal, nominal and Philox stream.  Returns the measurement as a dict."""
+    import torch
     from mppi_b200 import capi, synthetic as syn
     from mppi_b200.core import Core, make_state
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
     w = syn.WORKLOADS["C4"]
-    K, T, R = args.K or w.K, args.T or w.T, args.rovers
+    K, T, R = K or w.K, T or w.T, args.rovers
     pool = 16                                        # distinct synthetic maps; every rover gets its OWN copy in HBM
     rng = np.random.default_rng(7 + rank)
     dem_pool = torch.stack([syn.crater_dem(w.grid_size, w.half_width, seed=57 + i, device=dev) for i in range(pool)])
@@ -234,7 +507,7 @@ def run_rover_batch(args):
                            for i in range(pool)]).to(dev)
     idx = torch.arange(R, device=dev) % pool
     dems, cms = dem_pool[idx].contiguous(), cm_pool[idx].contiguous()
-    core = Core(K, T, device=local_rank, math=args.math, max_rovers=R)
+    core = Core(K, T, device=ctx.local_rank, math=args.math, max_rovers=R)
     core.set_terrain_batched(dems, w.half_width, cms)
     half = w.half_width / 2
     states = [make_state(float(rng.uniform(-half, half)), float(rng.uniform(-half, half)),
@@ -244,43 +517,25 @@ def run_rover_batch(args):
     states_host = torch.frombuffer(bytearray(bytes((capi.MppiState * R)(*states))), dtype=torch.uint8).pin_memory()
     states_dev = states_host.to(dev)
     cmd_host = torch.empty((R, 2), dtype=torch.float32).pin_memory()
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def timed(n, first):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
-        for i in range(n):
-            if not args.no_flush:
-                flush_buf.fill_(i & 0xff)
-            evs[i][0].record()
-            core.step_batched(states_dev, R, capi.PROJ_3D, 42, first + i)
-            evs[i][1].record()
-        torch.cuda.synchronize(dev)
-        return np.array([a.elapsed_time(b) for a, b in evs])
+    def one(i):
+        core.step_batched(states_dev, R, capi.PROJ_3D, 42, i)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    steps = min(args.steps, 100)
-    timed(max(3, min(args.warmup, 10)), 0)
-    sampler = ClockSampler(local_rank)
+    steps = min(args.steps if args.workload == "C4" else args.extras_steps, 100)
+    warm = max(3, min(args.warmup, 10))
+    ctx.timed_loop(one, warm, 0, ctx.do_flush)
+    sampler = ClockSampler(ctx.local_rank)
     sampler.start()
-    barrier()
-    per = timed(steps, 1000)
-    barrier()
+    ctx.barrier()
+    per = ctx.timed_loop(one, steps, 1000, ctx.do_flush)
+    ctx.barrier()
     clocks = sampler.stop()
-    total_ms = float(per.sum())
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms = total_ms / steps
+    ms = ctx.max_over_ranks(float(per.sum())) / steps
     # end to end: rover states from pinned host memory in, all commands back on the host, inside the timed region
     e2e_t = []
     for i in range(min(steps, 30)):
-        if not args.no_flush:
-            flush_buf.fill_(i & 0xff)
+        if ctx.do_flush:
+            ctx.flush_buf.fill_(i & 0xff)
             torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         states_dev.copy_(states_host, non_blocking=True)
@@ -288,43 +543,107 @@ def run_rover_batch(args):
         cmd_host.copy_(core.stats[:R, 6:8], non_blocking=True)
         torch.cuda.synchronize(dev)
         e2e_t.append(time.perf_counter() - t0)
-    e2e_mean = float(np.mean(e2e_t))
-    if world > 1:
-        t = torch.tensor([e2e_mean], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_mean = float(t.item())
-    if rank == 0:
+    e2e_mean = ctx.max_over_ranks(float(np.mean(e2e_t)))
+    # check: rover 0 of the batch against a stand-alone controller on rover 0's maps (same Philox stream: rover index
+    # 0): per-sample costs bit for bit, update within the summation-order tolerance (the two launches use different
+    # block shapes)
+    core.set_nominal(np.zeros((R, T), np.float32), np.zeros((R, T), np.float32), n_rovers=R)
+    core.step_batched(states_dev, R, capi.PROJ_3D, 42, 77)
+    torch.cuda.synchronize(dev)
+    costs_b = core.costs[0].cpu().numpy().copy()
+    u1_b = core.optimal_u1[0].cpu().numpy().copy()
+    solo = Core(K, T, device=ctx.local_rank, math=args.math)
+    solo.set_terrain(dems[0], w.half_width, cms[0])
+    solo.step(states[0], capi.PROJ_3D, None, 42, 77)
+    torch.cuda.synchronize(dev)
+    check = {"rover0_costs_bitwise": bool(np.array_equal(costs_b, solo.costs[0].cpu().numpy())),
+             "rover0_update_rel": rel_err(u1_b, solo.optimal_u1[0].cpu().numpy()),
+             "all_commands_finite": bool(torch.isfinite(core.stats[:R, 6:8]).all().item())}
+    check["passed"] = bool(check["rover0_costs_bitwise"] and check["rover0_update_rel"] < 1e-5 and check["all_commands_finite"])
+    check["passed"] = ctx.max_over_ranks(0.0 if check["passed"] else 1.0) == 0.0
+    solo.close()
+    units = R * K * T
+    dur = ms * 1e-3
+    res = {"workload": w.name, "rovers_per_gpu": R, "rovers_total": R * world, "K": K, "T": T, "steps": steps, "warmup": warm,
+           "ms_per_step": ms, "value": units * world / dur, "unit": "sample-steps/s", "rover_updates_per_s": R * world / dur,
+           "p50_us": float(np.median(per) * 1e3), "p99_us": float(np.percentile(per, 99) * 1e3),
+           "dem": f"{w.grid_size}x{w.grid_size} f32 per rover ({pool} distinct maps, one copy per rover)",
+           "costmap": f"{w.costmap_size}x{w.costmap_size} f32 per rover", "math": args.math,
+           "parallelism": f"rover-sharded x{world}, no communication",
+           "e2e": {"value": units * world / e2e_mean, "unit": "sample-steps/s", "h2d_bytes_per_step": R * STATE_BYTES,
+                   "d2h_bytes_per_step": R * CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6),
+                   "call": "pinned states H2D + mppi_step_batched + all (v*, w*) D2H + stream synchronise"},
+           "check": check, "clocks": clocks, "stats_rover0": core.read_stats(0)}
+    core.close()
+    return res
+
+
+def run_rover_batch_line(ctx, args):
+    """--workload C4: the rover-sharded batch as the top-level line."""
+    r = run_c4(ctx, args, args.K, args.T)
+    if ctx.rank == 0:
         pk = peaks()
-        units = R * K * T
-        dur = ms * 1e-3
-        fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        lp = live_peaks(ctx.local_rank)
+        units = r["rovers_per_gpu"] * r["K"] * r["T"]
+        dur = r["ms_per_step"] * 1e-3
         line = {
-            "metric": "MPPI sample-steps/s", "value": units * world / dur, "unit": "sample-steps/s", "n_gpus": world,
-            "steps": steps, "warmup": max(3, min(args.warmup, 10)), "ms_per_step": ms, "higher_is_better": True,
+            "metric": "MPPI sample-steps/s", "value": r["value"], "unit": "sample-steps/s", "n_gpus": ctx.world,
+            "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "rovers_per_gpu": R, "rovers_total": R * world, "K": K, "T": T,
-                       "dem": f"{w.grid_size}x{w.grid_size} f32 per rover ({pool} distinct maps, one copy per rover)",
-                       "costmap": f"{w.costmap_size}x{w.costmap_size} f32 per rover", "math": args.math,
-                       "l2": "flushed between timed iterations (256 MiB fill)" if not args.no_flush else "warm",
-                       "parallelism": f"rover-sharded x{world}, no communication"},
-            "latency_us": {"p50": float(np.median(per) * 1e3), "p99": float(np.percentile(per, 99) * 1e3)},
-            "rover_updates_per_s": R * world / dur,
-            "e2e": {"value": units * world / e2e_mean, "unit": "sample-steps/s", "h2d_bytes_per_step": R * STATE_BYTES,
-                    "d2h_bytes_per_step": R * CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6),
-                    "call": "pinned states H2D + mppi_step_batched + all (v*, w*) D2H + stream synchronise"},
-            "gpu_launches": steps,
-            "roofline": {"bound": "hbm", "achieved": GATHER_BYTES_PER_SAMPLE_STEP * units / dur / 1e9, "peak": pk["hbm_gbs"],
-                         "unit": "GB/s", "frac": GATHER_BYTES_PER_SAMPLE_STEP * units / dur / 1e9 / pk["hbm_gbs"],
-                         "traffic": None, "kernel": "mppi_fused_kernel<3D, Philox>, grid.y = rover",
-                         "fp32": {"achieved": FLOP_PER_SAMPLE_STEP * units / dur / 1e12, "unit": "TFLOP/s",
-                                  "peak": fp32_peak, "frac": FLOP_PER_SAMPLE_STEP * units / dur / 1e12 / fp32_peak}},
-            "clocks": clocks,
-            "stats_rover0": core.read_stats(0),
+            "config": {k: r[k] for k in ("workload", "rovers_per_gpu", "rovers_total", "K", "T", "dem", "costmap", "math",
+                                         "parallelism")} |
+                      {"l2": "flushed between timed iterations (256 MiB fill)" if ctx.do_flush else "warm"},
+            "latency_us": {"p50": r["p50_us"], "p99": r["p99_us"]},
+            "rover_updates_per_s": r["rover_updates_per_s"], "e2e": r["e2e"], "gpu_launches": r["steps"],
+            "roofline": roofline_object("mono", units, r["T"], dur, pk, lp, {}, 1.0,
+                                        "mppi_fused_kernel<3D, Philox>, grid.y = rover"),
+            "check": r["check"], "clocks": r["clocks"], "stats_rover0": r["stats_rover0"],
         }
         emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        if not r["check"]["passed"]:
+            sys.exit(3)
+
+
+def roofline_object(kernel_kind, units, T, dur_s, pk, lp, counters, share, kernel_name):
+    """The contract's roofline object for the dominant kernel.  `units` = sample-steps ONE launch processes on ONE GPU.
+    The path streams nothing through HBM (no K x T tensor exists) and its gathers are served by shared memory / L1 / L2,
+    so neither HBM nor the tensor cores bind it: `bound` names what does -- the dependent-issue LATENCY of one warp's
+    chain in the pipelined kernel (K of a few thousand), instruction ISSUE in the monolithic kernel (large K) -- and
+    the HBM / FP32 / issue / L2-gather fractions are sub-objects, each against a peak measured on this pool."""
+    hbm_ach = GATHER_BYTES_PER_SAMPLE_STEP * units / dur_s / 1e9
+    fp32_ach = FLOP_PER_SAMPLE_STEP * units / dur_s / 1e12
+    sect_ach = GATHER_SECTORS_PER_SAMPLE_STEP * units / dur_s / 1e9
+    issue_peak = 148 * 4 * pk["sm_max_mhz"] * 1e6
+    r = {
+        "bound": "latency" if kernel_kind == "pipe" else "issue",
+        "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
+        "traffic": counters.get("dram_bytes_per_launch"),
+        "kernel": kernel_name, "kernel_share_of_step": share,
+        "per_gpu": True, "sample_steps_per_launch": units,
+        "algorithmic_bytes_per_sample_step": GATHER_BYTES_PER_SAMPLE_STEP,
+        "peak_source": f"{pk['source']} MEASURED_PEAKS.json hbm_gbs",
+        "note": "achieved / peak / frac: algorithmic gather bytes against the measured HBM peak, as the contract asks; the "
+                "gathers are served on-chip (traffic = DRAM bytes per launch from ncu when the captured configuration "
+                "matches, else null), so this fraction is small by construction and `bound` is not 'hbm'",
+        "hbm": {"achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"]},
+        "fp32": {"achieved": fp32_ach, "peak": lp["fp32_tflops"], "unit": "TFLOP/s", "frac": fp32_ach / lp["fp32_tflops"],
+                 "flop_per_sample_step": FLOP_PER_SAMPLE_STEP, "peak_source": "measured live: " + lp["how"]},
+        "l2_gather": {"achieved": sect_ach, "peak": lp["l2_gather_gsectors"], "unit": "Gsector/s",
+                      "frac": sect_ach / lp["l2_gather_gsectors"],
+                      "sectors_per_sample_step": GATHER_SECTORS_PER_SAMPLE_STEP,
+                      "peak_source": "measured live (random 32-byte-sector gathers from L2)",
+                      "note": "upper bound of what the lookups would cost if none were staged in shared memory / L1"},
+    }
+    if kernel_kind == "pipe":
+        r["latency"] = {"ns_per_horizon_step": dur_s * 1e9 / T, "unit": "ns",
+                        "note": "the whole launch divided by T: the chain warp's dependent issue latency per horizon step "
+                                "plus the launch's fixed parts (tools/timeline.py splits them)"}
+    if counters.get("warp_inst_per_launch"):
+        ach = counters["warp_inst_per_launch"] / dur_s
+        r["issue"] = {"achieved": ach, "peak": issue_peak, "unit": "warp-inst/s", "frac": ach / issue_peak,
+                      "extrapolated": bool(counters.get("extrapolated")), "source": counters.get("source"),
+                      "peak_source": "148 SM x 4 schedulers x sm_max_mhz"}
+    return r
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -351,39 +670,32 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
-    if args.workload == "C4":
-        run_rover_batch(args)
-        return
 
     import torch
-    import torch.distributed as dist
     from mppi_b200 import capi
-    from mppi_b200.core import Core, make_state
-    from mppi_b200.sharding import SampleShardedStepper
+    from mppi_b200.core import make_state
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n_gpus = world
+    ctx = Ctx(args)
+    if args.workload == "C4":
+        run_rover_batch_line(ctx, args)
+        ctx.close()
+        return
+    dev, rank, n_gpus = ctx.dev, ctx.rank, ctx.world
 
-    w, dem_np, cm_np, start, goal = build_workload(args.workload, args.K, args.T, args.dem_noise)
+    w, dem_np, cm_np, start, goal, heading = build_workload(args.workload, args.K, args.T, args.dem_noise, args.start)
     K, T = w.K, w.T                       # per-GPU samples
     K_total = K * n_gpus
-    core = Core(K, T, device=local_rank, math=args.math,
-                variant={"auto": capi.VARIANT_AUTO, "mono": capi.VARIANT_MONO, "pipe": capi.VARIANT_PIPE}[args.variant],
-                **critic_weights(args))
     dem = torch.from_numpy(dem_np).to(dev)
     cm = torch.from_numpy(cm_np).to(dev)
-    core.set_terrain(dem, w.half_width, cm)
-    state = make_state(start[0], start[1], (1.0, 0.0, 0.0), goal_x=goal[0], goal_y=goal[1])
-    stepper = SampleShardedStepper(core, K_total, transport=args.exchange) if n_gpus > 1 else None
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    do_flush = not args.no_flush
+    state = make_state(start[0], start[1], heading, goal_x=goal[0], goal_y=goal[1])
+    core, stepper = make_sharded(ctx, K, T, dem, cm, w.half_width, args.exchange, math=args.math, variant=args.variant,
+                                 **critic_weights(args))
     seed = 42
+    lp = live_peaks(ctx.local_rank) if rank == 0 else None
+
+    # ---- the contract's timed region: W warm-up steps, then EXACTLY K steps, barrier + synchronise on both sides
+    sampler = ClockSampler(ctx.local_rank)
+    warm_n = max(3, args.warmup)
 
     def one_step(i):
         if stepper is None:
@@ -391,76 +703,80 @@ def main():
         else:
             stepper.step(state, capi.PROJ_3D, seed, i)
 
-    def timed_loop(n, first, flush):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
-        for i in range(n):
-            if flush:
-                flush_buf.fill_(i & 0xff)
-            evs[i][0].record()
-            one_step(first + i)
-            evs[i][1].record()
-        torch.cuda.synchronize(dev)
-        return np.array([a.elapsed_time(b) for a, b in evs], dtype=np.float64)     # ms each
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # warm-up
-    timed_loop(max(3, args.warmup), 0, do_flush)
-    sampler = ClockSampler(local_rank)
+    ctx.timed_loop(one_step, warm_n, 0, ctx.do_flush)
     sampler.start()
-    barrier()
+    ctx.barrier()
     t_wall0 = time.perf_counter()
-    per_step_ms = timed_loop(args.steps, 1000, do_flush)
-    barrier()
+    per_step_ms = ctx.timed_loop(one_step, args.steps, 1000, ctx.do_flush)
+    ctx.barrier()
     wall_s = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    total_ms = float(per_step_ms.sum())
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = ctx.max_over_ranks(float(per_step_ms.sum())) / args.steps
     value = K_total * T / (ms_per_step * 1e-3)
 
-    # steady-state (L2 warm) numbers for context
-    warm_ms = timed_loop(args.steps, 5000, False)
+    # ---- latency leg: >= 1000 back-to-back iterations whatever --steps is, same protocol
+    ctx.barrier()
+    lat_ms = ctx.timed_loop(one_step, max(args.latency_steps, 1), 100000, ctx.do_flush)
+    clocks = sampler.stop()
+    # steady state (L2 warm) for context
+    warm_ms = ctx.timed_loop(one_step, min(max(args.steps, 100), 1000), 200000, False)
 
-    # end-to-end through the host-facing call: host state in, host (v, w) out, D2H + sync inside the timed region
-    e2e = None
+    # ---- share of the step spent in the fused kernel: the library's own events around the launch vs ours
+    share = None
+    if n_gpus == 1:
+        capi.check(core.L.mppi_enable_timing(core.h, 1), "mppi_enable_timing")
+        ours, theirs = [], []
+        us = C.c_float()
+        for i in range(50):
+            if ctx.do_flush:
+                ctx.flush_buf.fill_(i & 0xff)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            one_step(300000 + i)
+            e1.record()
+            capi.check(core.L.mppi_last_step_us(core.h, C.byref(us)), "mppi_last_step_us")
+            torch.cuda.synchronize(dev)
+            ours.append(e0.elapsed_time(e1) * 1e3)
+            theirs.append(us.value)
+        capi.check(core.L.mppi_enable_timing(core.h, 0), "mppi_enable_timing")
+        share = float(np.sum(theirs) / np.sum(ours))
+
+    # ---- end to end through the host-facing call: host state in, host (v, w) out inside the timed region
+    e2e_steps = max(args.steps, 200) if n_gpus == 1 else min(max(args.steps, 100), 300)
     if n_gpus == 1:
         for i in range(5):
             core.step_host(state, capi.PROJ_3D, seed, 9000 + i)
         e2e_t = []
-        for i in range(args.steps):
-            if do_flush:
-                flush_buf.fill_(i & 0xff)
+        for i in range(e2e_steps):
+            if ctx.do_flush:
+                ctx.flush_buf.fill_(i & 0xff)
                 torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             core.step_host(state, capi.PROJ_3D, seed, 10000 + i)
             e2e_t.append(time.perf_counter() - t0)
         e2e_t = np.array(e2e_t)
-        e2e = {"value": K * T / float(e2e_t.mean()), "unit": "sample-steps/s", "h2d_bytes_per_step": STATE_BYTES,
-               "d2h_bytes_per_step": CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6),
-               "p99_us": float(np.percentile(e2e_t, 99) * 1e6),
-               "call": "mppi_step_host (C ABI): MppiState by value from host memory, 8-byte pinned D2H of the "
-                       "command, stream synchronise"}
+        e2e_mean = float(e2e_t.mean())
+        call = ("mppi_step_host (C ABI): MppiState by value from host memory; the kernel stores the 8-byte command into "
+                "mapped pinned host memory as soon as it exists, the host polls its sequence word")
     else:
-        # the sharded step's result is read back on every rank
+        # the sharded step's command is read back on every rank; the ranks run in lock step because every step needs
+        # every rank's partials, so a barrier per step would only add its own skew
+        for i in range(5):
+            stepper.step_host(state, capi.PROJ_3D, seed, 9000 + i)
+        ctx.barrier()
         e2e_t = []
-        for i in range(min(args.steps, 100)):
-            if do_flush:
-                flush_buf.fill_(i & 0xff)
-            barrier()
+        for i in range(e2e_steps):
+            if ctx.do_flush:
+                ctx.flush_buf.fill_(i & 0xff)
+                torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             stepper.step_host(state, capi.PROJ_3D, seed, 20000 + i)
             e2e_t.append(time.perf_counter() - t0)
-        t = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": K_total * T / float(t.item()), "unit": "sample-steps/s", "h2d_bytes_per_step": STATE_BYTES,
-               "d2h_bytes_per_step": CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6)}
+        e2e_t = np.array(e2e_t)
+        e2e_mean = ctx.max_over_ranks(float(e2e_t.mean()))
+        call = "mppi_step_sharded_host on every rank (same zero-copy command store), max over ranks of the mean"
+    e2e = {"value": K_total * T / e2e_mean, "unit": "sample-steps/s", "h2d_bytes_per_step": STATE_BYTES,
+           "d2h_bytes_per_step": CMD_BYTES, "p50_us": float(np.median(e2e_t) * 1e6),
+           "p99_us": float(np.percentile(e2e_t, 99) * 1e6), "steps": int(e2e_steps), "call": call}
 
     # f2: the offline closed loop of MPPI_Controller.run resident on the device (one launch per iteration, plant step
     # and feedback logic inside the kernel) vs the same loop driven from the host with a read-back per iteration.
@@ -494,74 +810,79 @@ def main():
                        "reference_published_us_per_loop": 3000.0,
                        "note": "MPPI_Controller.run (MPPI_isaac.py:755-805): plant = the controller's own model; "
                                "reference figure: 'work summarise':71 (K=1000, T=100, unspecified GPU)"}
+    stats = core.read_stats()
+    core.close()
 
+    # ---- same run: equality check of the sharded controller, BASELINE configs 3 and 4
+    extras = (not args.no_extras) and args.workload == "C2" and not (args.K or args.T)
+    sharded_check = c3 = c4 = None
+    if extras:
+        sharded_check = equality_check(ctx, K, T, dem, cm, w.half_width, state, math=args.math)
+        c3 = run_c3(ctx, args)
+        c4 = run_c4(ctx, args)
+        for k in ("clocks", "stats_rover0"):
+            c4.pop(k, None)
+
+    failed = False
     if rank == 0:
         pk = peaks()
-        # Contract object: algorithmic gather bytes against the MEASURED HBM peak.  The path is served from L1/L2
-        # and is latency- (small K) or issue-bound (large K), so this fraction is small by construction; the `fp32`
-        # and `issue` sub-objects are the resources that actually bind.
-        dur_s = ms_per_step * 1e-3
-        fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12          # TFLOP/s, FFMA
-        achieved_tflops = FLOP_PER_SAMPLE_STEP * K * T / dur_s / 1e12
-        hbm_achieved = GATHER_BYTES_PER_SAMPLE_STEP * K * T / dur_s / 1e9
-        counters = kernel_counters(w.name.split()[0], args.math)
-        roofline = {
-            "bound": "hbm", "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": hbm_achieved / pk["hbm_gbs"],
-            "traffic": counters.get("dram_bytes_per_launch"),
-            "kernel": "mppi_fused_pipe_kernel<3D, Philox>" if K <= 148 * 32 * 2 and args.variant != "mono"
-                      else "mppi_fused_kernel<3D, Philox>",
-            "kernel_share_of_step": 1.0,
-            "algorithmic_bytes_per_sample_step": GATHER_BYTES_PER_SAMPLE_STEP,
-            "peak_source": f"{pk['source']} MEASURED_PEAKS.json hbm_gbs",
-            "note": "gathers are served by L1/L2 (ncu: DRAM traffic per launch is `traffic`, far below the algorithmic "
-                    "bytes); the kernel is bound by dependent-issue latency at K=4096 and by instruction issue at "
-                    "large K, see fp32 / issue",
-            "fp32": {"achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak,
-                     "flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
-                     "peak_source": "148 SM x 128 FP32 lanes x 2 x sm_max_mhz (no FP32 figure in MEASURED_PEAKS.json)"},
-        }
-        if counters.get("warp_inst_per_launch"):
-            issue_peak = 148 * 4 * pk["sm_max_mhz"] * 1e6
-            issue_ach = counters["warp_inst_per_launch"] / dur_s
-            roofline["issue"] = {"achieved": issue_ach, "peak": issue_peak, "unit": "warp-inst/s",
-                                 "frac": issue_ach / issue_peak, "source": counters.get("source")}
+        pipe = (K <= PIPE_MAX_SAMPLES and args.variant != "mono") or args.variant == "pipe"
+        kind = "pipe" if pipe else "mono"
+        counters = kernel_counters(w.name.split()[0], args.math, K, T, kind) if n_gpus == 1 else {}
+        kname = ("mppi_fused_pipe_kernel<3D, Philox> (128 worker blocks + 1 updater block)" if pipe
+                 else "mppi_fused_kernel<3D, Philox>")
+        roofline = roofline_object(kind, K * T, T, ms_per_step * 1e-3, pk, lp, counters,
+                                   share if share is not None else None, kname)
         line = {
             "metric": "MPPI sample-steps/s", "value": value, "unit": "sample-steps/s", "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": warm_n, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "K_per_gpu": K, "K_total": K_total, "T": T,
                        "dem": f"{w.grid_size}x{w.grid_size} f32", "costmap": f"{w.costmap_size}x{w.costmap_size} f32",
                        "math": args.math, "variant": args.variant, "noise": "in-kernel Philox4x32-10 + Box-Muller", "proj": "3d",
                        "critics": ("reference 4 (path, wheel slope, speed, obstacle) + body-slope, roll, pitch"
                                    if critic_weights(args) else "reference 4 (path, wheel slope, speed, obstacle)"),
-                       "l2": "flushed between timed iterations (256 MiB fill)" if do_flush else "warm",
+                       "scene": ("the reference's start (-60.57, -60.23) -> goal (65.8, 65.4): flat ground outside the rock "
+                                 "field, no lethal cell within reach (the rock-field case: --start rocks, and the C2rock "
+                                 "golden test)" if args.start == "bench" else
+                                 "start inside the rock field on a crater wall (lethal cells and slopes within reach)"),
+                       "l2": "flushed between timed iterations (256 MiB fill)" if ctx.do_flush else "warm",
                        "parallelism": "single GPU" if n_gpus == 1 else
-                       (f"sample-sharded x{n_gpus}, {core.partial_floats() * 4} B softmax partial per rank exchanged "
-                        + ("inside the fused launch over NVLink peer memory (CUDA IPC), no collective call"
-                           if args.exchange == "p2p" else "with one NCCL all-gather + combine kernel"))},
-            "latency_us": {"p50": float(np.median(per_step_ms) * 1e3), "p99": float(np.percentile(per_step_ms, 99) * 1e3),
-                           "mean": float(per_step_ms.mean() * 1e3), "max": float(per_step_ms.max() * 1e3),
-                           "argmax_step": int(per_step_ms.argmax()),
-                           "steps_over_2x_p50": int((per_step_ms > 2 * np.median(per_step_ms)).sum())},
+                       (f"sample-sharded x{n_gpus}; softmax partial per block exchanged "
+                        + ("inside the fused launch over NVLink peer memory (CUDA IPC; flag-in-data lines, no collective "
+                           "call, no fence)" if args.exchange == "p2p" else "with one NCCL all-gather + combine kernel"))},
+            "latency_us": {"p50": float(np.median(lat_ms) * 1e3), "p99": float(np.percentile(lat_ms, 99) * 1e3),
+                           "mean": float(lat_ms.mean() * 1e3), "max": float(lat_ms.max() * 1e3), "steps": int(len(lat_ms)),
+                           "steps_over_2x_p50": int((lat_ms > 2 * np.median(lat_ms)).sum()),
+                           "timed_region_p50": float(np.median(per_step_ms) * 1e3),
+                           "note": "device time of back-to-back launches on this rank (CUDA events), L2 flushed between them"},
             "warm_l2": {"ms_per_step": float(warm_ms.mean()), "p50_us": float(np.median(warm_ms) * 1e3),
                         "value": K_total * T / float(warm_ms.mean() * 1e-3)},
             "e2e": e2e,
             "gpu_launches": args.steps * (1 if (n_gpus == 1 or args.exchange == "p2p") else 2),
             "roofline": roofline,
+            "measured_peaks_live": lp,
             "closed_loop": closed_loop,
             "clocks": clocks,
             "wall_s": wall_s,
-            "stats": core.read_stats(),
+            "stats": stats,
         }
+        if extras:
+            line["sharded_check"] = sharded_check
+            line["c3"] = c3
+            line["c4"] = c4
+            failed = (not sharded_check["passed"] or not c4["check"]["passed"]
+                      or any(not c3[m]["check"]["passed"] for m in ("weak", "strong") if "check" in c3[m]))
         if n_gpus == 1 and not args.no_cpu_baseline:
             base, _ = cpu_reference_run(w, dem_np, cm_np, start, goal, seconds=args.cpu_seconds,
-                                        critics=critic_weights(args))
+                                        critics=critic_weights(args), heading=heading)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["reference_script"] = cpu_reference_script_run(w)
         emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
+    if failed:
+        sys.stderr.write("bench.py: an equality check FAILED (see sharded_check / c3 / c4 in the line)\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

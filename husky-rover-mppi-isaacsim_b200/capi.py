@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(_HERE, "libmppi_b200.
 CSRC = os.path.join(_HERE, "csrc")
 
 MPPI_OK = 0
+ABI_VERSION = 4
 PROJ_2D = 2
 PROJ_3D = 3
 MATH_STRICT = 0
@@ -110,6 +111,8 @@ SYMBOLS = {
     "mppi_enable_timing": (C.c_int, [_H, C.c_int32]),
     "mppi_last_step_us": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "mppi_set_trace": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
+    "mppi_measure_peaks": (C.c_int, [C.c_int32, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                     C.POINTER(C.c_float)]),
     "mppi_test_detmath": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mppi_test_noise": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -148,11 +151,14 @@ def lib() -> C.CDLL:
             raise MppiError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(the MPPI core has no CPU fallback)")
         L = C.CDLL(LIB_PATH)
+        ab = bool(os.environ.get("MPPI_B200_LIB"))       # A/B against an older build: newer entry points may be absent
         for name, (res, args) in SYMBOLS.items():
+            if ab and not hasattr(L, name):
+                continue
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.mppi_abi_version() != 3:
+        if L.mppi_abi_version() != ABI_VERSION and not ab:
             raise MppiError("libmppi_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -28,6 +28,12 @@ struct MppiHandle {
     float *nominal1, *nominal2, *prev1, *prev2, *opt_v, *opt_w, *costs, *partials, *stats, *sim_traj, *sim_heading;
     float* dbg_costs;
     unsigned int* counters;
+    // LL protocol of the pipelined kernel (mppi_kernels.cuh): per-block partial lines, polled by the updater block
+    uint4* ll;                   // device [ll_slots][ll_lines(T_cap)] lines, grown on demand
+    size_t ll_slots;
+    unsigned long long* minkey;  // device [max_rovers]
+    uint32_t ll_seq;             // sequence number of the last LL launch (1 .. 2^31 - 1)
+    uint32_t spin_limit_ms;      // MPPI_SPIN_LIMIT_MS: how long a kernel may wait for another block / rank before it traps
     float* cmd_pinned;      // host pinned + mapped [4]: {v*, w*, sequence, 0}, written by the kernel itself
     float* cmd_pinned_dev;  // device view of cmd_pinned
     uint32_t host_seq;
@@ -36,7 +42,9 @@ struct MppiHandle {
     bool timed_valid;
     unsigned long long* trace;   // optional device buffer for kernel timeline stamps (mppi_set_trace)
     // sample-sharded multi-GPU exchange over peer memory (mppi_comm_*)
-    void* comm_local;            // this rank's exchange allocation: [2][world][stride] floats + [2][world] flags
+    void* comm_local;            // this rank's exchange allocation: [LL lines (flat variant)] + [2][world][stride] floats + [2][world] flags
+    size_t comm_ll_bytes;        // size of the LL region (0: laid out for the two-level variant only)
+    size_t comm_bytes;
     void* comm_peer[kMaxRanks];  // peers' allocations opened with CUDA IPC (nullptr for this rank)
     PeerComm peers;
     int comm_nblocks;            // blocks per rank the exchange buffers were laid out for
@@ -99,7 +107,7 @@ extern "C" int mppi_default_params(MppiParams* p, int32_t K, int32_t T)
     return MPPI_OK;
 }
 
-// Variant + block size.  Small K is latency-bound: the warp-specialised kernel (32 samples per 4-warp CTA) wins
+// Variant + block size.  Small K is latency-bound: the warp-specialised kernel (32 samples per six-warp CTA) wins
 // while the grid fits the machine a few times over; large K wants the monolithic kernel with full CTAs.
 // What counts is the number of samples in flight in the launch: K per rover x rovers.
 static void pick_launch(const MppiParams& p, int n_rovers, int* block, int* nblocks, bool* pipe)
@@ -107,7 +115,7 @@ static void pick_launch(const MppiParams& p, int n_rovers, int* block, int* nblo
     const int K = p.K;
     const long long total = (long long)K * (n_rovers > 0 ? n_rovers : 1);
     *pipe = (p.variant == MPPI_VARIANT_PIPE || (p.variant == MPPI_VARIANT_AUTO && total <= 148 * 32 * 2));
-    if (*pipe) { *block = 128; *nblocks = (K + 31) / 32; return; }
+    if (*pipe) { *block = 192; *nblocks = (K + 31) / 32; return; }
     int b;
     if (total <= 148 * 32 * 2) b = 32;
     else if (total <= 148 * 64 * 8) b = 64;
@@ -163,6 +171,9 @@ extern "C" int mppi_create(const MppiParams* params, int32_t device, int32_t max
     alloc(&h->dbg_costs, K);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->counters, R * kCounterStride * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(h->counters, 0, R * kCounterStride * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->minkey, R * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->minkey, 0, R * sizeof(unsigned long long));
+    if (const char* lim = getenv("MPPI_SPIN_LIMIT_MS")) h->spin_limit_ms = (uint32_t)strtoul(lim, nullptr, 10);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->cmd_pinned, 4 * sizeof(float), cudaHostAllocMapped);
     if (e == cudaSuccess) { memset(h->cmd_pinned, 0, 4 * sizeof(float)); e = cudaHostGetDevicePointer((void**)&h->cmd_pinned_dev, h->cmd_pinned, 0); }
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
@@ -185,6 +196,8 @@ extern "C" int mppi_destroy(MppiHandle* h)
     if (h->loop_ctl) cudaFree(h->loop_ctl);
     if (h->loop_log) cudaFree(h->loop_log);
     if (h->counters) cudaFree(h->counters);
+    if (h->ll) cudaFree(h->ll);
+    if (h->minkey) cudaFree(h->minkey);
     if (h->cmd_pinned) cudaFreeHost(h->cmd_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -325,10 +338,36 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
     if (to_host) { a.host_cmd = h->cmd_pinned_dev; a.host_seq = ++h->host_seq; }
     if (sharded) { a.peers = h->peers; a.peers.seq = ++h->peers.seq; }
     if (loop) a.loop = *loop;
+    a.spin_limit_ms = h->spin_limit_ms;
+    if (h->pipe) {
+        // LL protocol: one slot of lines per worker block (grown on demand; first step only), a launch sequence number
+        // that is never 0.  A flat sharded step takes its sequence number from the exchange (identical on all ranks)
+        // and tags its running-minimum entries in the upper half of the tag space.
+        if (sharded && !h->peers.ll[h->peers.rank]) return MPPI_ERR_UNSUPPORTED;      // buffers laid out for two-level
+        const size_t need = (size_t)n_rovers * h->nblocks;
+        if (h->ll_slots < need) {
+            CK(cudaStreamSynchronize(s));
+            if (h->ll) CK(cudaFree(h->ll));
+            h->ll = nullptr; h->ll_slots = 0;
+            const size_t bytes = need * ll_lines(h->T_cap) * sizeof(uint4);
+            CK(cudaMalloc((void**)&h->ll, bytes));
+            CK(cudaMemset(h->ll, 0, bytes));
+            h->ll_slots = need;
+        }
+        if (h->ll_seq >= 0x7fffffffu) {                      // wrap: stale lines / keys must not look current again
+            CK(cudaMemsetAsync(h->ll, 0, h->ll_slots * ll_lines(h->T_cap) * sizeof(uint4), s));
+            CK(cudaMemsetAsync(h->minkey, 0, (size_t)h->max_rovers * sizeof(unsigned long long), s));
+            h->ll_seq = 0;
+        }
+        ++h->ll_seq;
+        a.ll = h->ll; a.minkey = h->minkey;
+        a.ll_seq = sharded ? a.peers.seq : h->ll_seq;
+        a.mk_tag = sharded ? (a.peers.seq | 0x80000000u) : h->ll_seq;
+    }
     if (h->pipe && !states_dev && n_rovers == 1 && proj == MPPI_PROJ_3D && h->nblocks <= 148)
     {
         a.tile = plan_dem_tile(h->p, h->terrain,
-                               MPPI_BY_NS(h->p, pipe_smem_bytes_no_tile(h->p.T, h->nblocks * (a.peers.world > 0 && h->nblocks <= 148 ? a.peers.world : 1))));
+                               MPPI_BY_NS(h->p, pipe_smem_bytes_no_tile(h->p.T, h->nblocks * (a.peers.world > 0 ? a.peers.world : 1))));
         if (a.tile.w > 0) {
             if (encode_dem_desc(h, h->terrain, a.tile.w, a.tile.h)) a.dem_desc = h->dem_desc;
             else a.tile.w = a.tile.h = 0;
@@ -416,7 +455,9 @@ extern "C" int mppi_combine_partials(MppiHandle* h, const MppiState* state, cons
 }
 
 // ---------------------------------------------------------------- sample-sharded step over peer memory
-static size_t comm_floats(int world, int nblocks, int T) { return (size_t)2 * world * nblocks * partial_stride(T); }
+// Exchange allocation of one rank: [LL region: 2 parities x world x nblocks slots of ll_lines(T) lines -- flat variant,
+// pipelined kernel only] [2 x world rank partials of partial_stride(T) floats] [2 x world arrival flags].
+static size_t comm_floats(int world, int T) { return (size_t)2 * world * partial_stride(T); }
 
 extern "C" int mppi_comm_export(MppiHandle* h, int32_t world, unsigned char* ipc_handle_out)
 {
@@ -425,9 +466,10 @@ extern "C" int mppi_comm_export(MppiHandle* h, int32_t world, unsigned char* ipc
     if (h->comm_local) return MPPI_ERR_INVALID_ARG;             // already exported
     pick_launch(h->p, 1, &h->block, &h->nblocks, &h->pipe);
     h->comm_nblocks = h->nblocks;
-    const size_t bytes = comm_floats(world, h->comm_nblocks, h->T_cap) * sizeof(float) + (size_t)2 * world * sizeof(unsigned);
-    CK(cudaMalloc(&h->comm_local, bytes));
-    CK(cudaMemset(h->comm_local, 0, bytes));
+    h->comm_ll_bytes = h->pipe ? (size_t)2 * world * h->comm_nblocks * ll_lines(h->T_cap) * sizeof(uint4) : 0;
+    h->comm_bytes = h->comm_ll_bytes + comm_floats(world, h->T_cap) * sizeof(float) + (size_t)2 * world * sizeof(unsigned);
+    CK(cudaMalloc(&h->comm_local, h->comm_bytes));
+    CK(cudaMemset(h->comm_local, 0, h->comm_bytes));
     CK(cudaDeviceSynchronize());
     cudaIpcMemHandle_t mh;
     CK(cudaIpcGetMemHandle(&mh, h->comm_local));
@@ -441,7 +483,12 @@ extern "C" int mppi_comm_connect(MppiHandle* h, int32_t rank, int32_t world, con
     if (!h || !h->comm_local || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !ipc_handles)
         return MPPI_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (h->comm_peer[r]) { cudaIpcCloseMemHandle(h->comm_peer[r]); h->comm_peer[r] = nullptr; }
     memset(&h->peers, 0, sizeof(h->peers));
+    // the sequence numbers restart at 1: lines / flags of an earlier connection must not look current
+    CK(cudaMemset(h->comm_local, 0, h->comm_bytes));
+    CK(cudaDeviceSynchronize());
     for (int r = 0; r < world; ++r) {
         void* base = h->comm_local;
         if (r != rank) {
@@ -450,8 +497,10 @@ extern "C" int mppi_comm_connect(MppiHandle* h, int32_t rank, int32_t world, con
             CK(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
             h->comm_peer[r] = base;
         }
-        h->peers.x[r] = static_cast<float*>(base);
-        h->peers.f[r] = reinterpret_cast<unsigned*>(static_cast<float*>(base) + comm_floats(world, h->comm_nblocks, h->T_cap));
+        char* b = static_cast<char*>(base);
+        h->peers.ll[r] = h->comm_ll_bytes ? reinterpret_cast<uint4*>(b) : nullptr;
+        h->peers.x[r] = reinterpret_cast<float*>(b + h->comm_ll_bytes);
+        h->peers.f[r] = reinterpret_cast<unsigned*>(h->peers.x[r] + comm_floats(world, h->T_cap));
     }
     h->peers.rank = rank;
     h->peers.world = world;
@@ -626,7 +675,7 @@ extern "C" int mppi_set_trace(MppiHandle* h, uint64_t* trace_dev, int32_t* nbloc
 {
     if (!h) return MPPI_ERR_INVALID_ARG;
     h->trace = reinterpret_cast<unsigned long long*>(trace_dev);
-    if (nblocks_out) *nblocks_out = h->nblocks;
+    if (nblocks_out) *nblocks_out = h->nblocks + (h->pipe ? 1 : 0);      // the pipelined launch has an updater block
     return MPPI_OK;
 }
 

@@ -17,15 +17,33 @@ constexpr int kMaxBlock = 256;        // threads per block upper bound
 constexpr int kStatsStride = 8;       // floats per rover in the stats buffer
 constexpr int kCounterStride = 4;     // uints per rover: {ticket, oob, nan, running-minimum key of the block minima}
 
+// ---------------------------------------------------------------- flag-in-data ("LL") softmax partials
+// The pipelined kernel (latency regime) hands its block partials to a designated UPDATER block -- block `nblocks` of
+// the grid, resident on an otherwise idle SM -- as 16-byte lines {value0, seq, value1, seq}: every 8-byte half carries
+// the launch's sequence number, so a line is valid exactly when both halves show the current `seq` (8-byte stores are
+// single transactions; the scheme of the low-latency collectives).  No ticket atomic, no release fence, no separate flag
+// round and nothing to re-arm between launches: a worker block stores its lines and exits, the updater polls them.
+// Slot layout (lines of 16 bytes):
+//   0  {min cost m_b, argmin (int bits)}      1  {sum w, sum w^2}      2  {out-of-range count, NaN count}      3  unused
+//   4 .. 4+P-1     {A1[2p], A1[2p+1]}         4+P .. 4+2P-1  {A2[2p], A2[2p+1]}        P = ceil(T / 2) step pairs
+// A block that can prove its partial will be scaled by exactly 0 (partial_is_dead) publishes lines 0-2 only, with
+// sum w = 0; the updater never reads the A lines of a slot whose sum w is 0.
+constexpr int kLLHeaderLines = 4;
+__host__ __device__ inline int ll_pairs(int T) { return (T + 1) >> 1; }
+__host__ __device__ inline int ll_lines(int T) { return kLLHeaderLines + 2 * ll_pairs(T); }
+
 // Peer exchange of the sample-sharded multi-GPU step (one process per GPU; buffers mapped with CUDA IPC).
-// Rank r owns x[r]: [2 parities][world][nblocks][partial_stride(T)] floats and f[r]: [2][world] arrival flags.  EVERY
-// block of rank g's fused kernel stores its softmax partial into slot (g, block) of every rank's buffer over NVLink as
-// soon as it has it; the rank's last block then releases one flag per peer, waits for the world's flags in its own
-// buffer and folds all world x nblocks partials in global block (= global sample) order, exactly as an unsharded run
-// over the same blocks would: compute + exchange + update in ONE launch, no collective library call, no second kernel,
-// one combine.
+// FLAT variant (pipelined kernel): rank r owns ll[r]: [2 parities][world][nblocks][ll_lines(T)] lines.  EVERY worker
+// block of rank g stores its LL partial into slot (g, block) of every rank's buffer over NVLink as soon as it has it
+// (dead partials: 3 lines per peer); every rank's updater block polls all world x nblocks slots in its OWN memory and
+// folds them in global block (= global sample) order, exactly as an unsharded run over the same blocks would: compute
+// + exchange + update in ONE launch, no collective library call, no second kernel, no system-scope fence.  The parity
+// half = seq & 1 keeps a rank that runs one step ahead from overwriting lines its neighbour is still reading.
+// TWO-LEVEL variant (monolithic kernel, thousands of blocks): the rank folds its own partials first, only the rank
+// partial crosses NVLink (x[r]: [2][world][partial_stride] floats + f[r]: [2][world] arrival flags).
 constexpr int kMaxRanks = 8;
 struct PeerComm {
+    uint4* ll[kMaxRanks];             // flat variant (nullptr when the buffers were laid out for the two-level one)
     float* x[kMaxRanks];
     unsigned int* f[kMaxRanks];
     int32_t rank, world;              // world == 0: no peer exchange
@@ -48,7 +66,7 @@ struct LoopCtl {
 };
 
 // Shared-memory DEM tile of the pipelined kernel (latency regime): the square of cells the body can reach, copied
-// once per CTA by TMA bulk copies (one per tile row) while the pipeline fills; the chain warp's four corner gathers
+// once per CTA by ONE 2-D TMA tensor copy while the pipeline fills; the chain warp's four corner gathers
 // per step then hit shared memory (4-byte bank granularity) instead of L1 (128-byte line granularity).  Geometry is
 // computed on the host from the same state the kernel gets.  w == 0: no tile (gathers go through L1 / L2).
 struct DemTile {
@@ -81,12 +99,20 @@ struct FusedArgs {
     uint64_t seed, offset;
     uint32_t k_begin;                 // first global sample id of this rank
     int32_t nblocks;                  // grid.x
-    unsigned long long* trace;        // optional device [nblocks][16] %globaltimer stamps (profiling aid), or nullptr
+    unsigned long long* trace;        // optional device [grid.x][32] %globaltimer stamps (profiling aid), or nullptr
     float* host_cmd;                  // optional mapped pinned host memory [4]: {v*, w*, sequence, 0} (mppi_step_host)
     uint32_t host_seq;                // sequence number stored with the command
     PeerComm peers;                   // sample-sharded multi-GPU exchange (world == 0: off)
+    // LL protocol of the pipelined kernel (see above): grid.x = nblocks + 1, block `nblocks` is the updater
+    uint4* ll;                        // device [n_rovers][nblocks][ll_lines(T)] lines (single-GPU launches)
+    unsigned long long* minkey;       // device [n_rovers]: (seq << 32) | order-reversed key of the lowest block minimum
+    uint32_t ll_seq;                  // sequence number of this launch (never 0); 0: legacy ticket protocol
+    uint32_t mk_tag;                  // tag of this launch's entries in `minkey` (entries with another tag are stale)
+    uint32_t spin_limit_ms;           // a wait for lines / flags that lasts longer traps (a missing rank must fail loudly)
     LoopCtl loop;                     // device-resident closed loop (state == nullptr: off)
     DemTile tile;                     // pipelined kernel only
+    int32_t uhist;                    // pipelined kernel: 1 = the block keeps its sampled u in shared memory ([T][2][32]
+                                      // floats after the DEM tile) for the A rows of the update; set by the launcher
     TmaDesc dem_desc;                 // valid when tile.w > 0
 };
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MPPI_B200_ABI_VERSION 3
+#define MPPI_B200_ABI_VERSION 4
 
 enum {
     MPPI_OK = 0,
@@ -200,10 +200,13 @@ int mppi_partial_floats(int32_t T);   /* 4 + 2T */
  *   1. every rank: mppi_comm_export(h, world, handle)        -> 64-byte CUDA IPC handle of its exchange buffer
  *   2. the ranks all-gather the handles (any host transport; sharding.py uses torch.distributed)
  *   3. every rank: mppi_comm_connect(h, rank, world, handles)   with handles = world x 64 bytes, in rank order
- *   4. per iteration, on every rank: mppi_step_sharded(...)  -- every block of the launch stores its softmax partial
- *      into every rank's buffer; the rank's last block releases a flag per peer, waits (bounded; traps on a missing
- *      rank) for the world's flags and folds all world x nblocks partials in global block order, so all ranks finish
- *      with the identical nominal and command -- bitwise what one GPU would compute over the same blocks.
+ *   4. per iteration, on every rank: mppi_step_sharded(...).  Latency regime (pipelined kernel): every worker block
+ *      stores its softmax partial as flag-in-data lines {value, sequence} into every rank's buffer (a partial that is
+ *      provably weightless: 48 bytes per peer); every rank's updater block polls the world x nblocks slots in its own
+ *      memory and folds them in global block order -- no ticket, no fence, no flag round, bitwise what one GPU computes
+ *      over the same blocks.  Throughput regime (monolithic kernel): the rank folds its own partials, the rank partials
+ *      are exchanged with one flag per peer and folded in rank order.  A rank that never arrives makes the others trap
+ *      after MPPI_SPIN_LIMIT_MS (environment, default 10000 ms of wall time) instead of hanging the GPUs.
  * All ranks must call mppi_step_sharded the same number of times. */
 int mppi_comm_export(MppiHandle *h, int32_t world, unsigned char *ipc_handle_out /* [64] */);
 int mppi_comm_connect(MppiHandle *h, int32_t rank, int32_t world, const unsigned char *ipc_handles);
@@ -273,10 +276,18 @@ int mppi_last_step_us(MppiHandle *h, float *us);
 
 /* Profiling aid: when trace_dev != NULL every block of rover 0 stores 32 64-bit words per step: slots 0-6 and 8-15
  * are %globaltimer nanoseconds of the kernel's phases (entry, set-up done, rollout start / end, roles joined, partial
- * published, update finished, cost ready, block softmax, ticket, and the last block's update phases), slot 7 the SM id,
- * slots 16-24 SM-clock stamps inside the last block's update (tools/timeline.py decodes them).  trace_dev: device
- * [nblocks * 32] uint64 (nblocks is returned through nblocks_out); NULL switches the stamps off (default). */
+ * published, update finished, cost ready, block softmax, rows published, and the update phases), slot 7 the SM id,
+ * slots 16-28 SM-clock stamps inside the update (tools/timeline.py decodes them).  trace_dev: device [rows * 32] uint64;
+ * rows is returned through nblocks_out (the pipelined launch has one more block than partials: its last block is the
+ * updater); NULL switches the stamps off (default). */
 int mppi_set_trace(MppiHandle *h, uint64_t *trace_dev, int32_t *nblocks_out);
+
+/* Measurement aid (no reference counterpart): two roofline denominators of the device the bench runs on that the
+ * driver-written MEASURED_PEAKS.json does not carry -- FP32 FMA throughput (TFLOP/s, independent FFMA chains on every
+ * sub-partition) and the L2 gather rate (random 4-byte gathers from an L2-resident window of l2_window_bytes >= 1 MiB:
+ * 1e9 32-byte sectors per second, and the same in GB/s).  Synchronous; allocates and frees its own scratch. */
+int mppi_measure_peaks(int32_t device, uint64_t l2_window_bytes, float *fp32_tflops, float *l2_gather_gsectors,
+                       float *l2_gather_gbs);
 
 /* Test hook: evaluates the specified ("det") math on the device. fn: 0 sincos, 1 sincos(2*pi*u), 2 log, 3 exp, 4 atan.
  * x, y0, y1 are device pointers [n]. */

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound(capi):
 
 def test_abi_version_and_strerror(capi):
     lib = capi.lib()
-    assert lib.mppi_abi_version() == 3
+    assert lib.mppi_abi_version() == 4
     assert lib.mppi_strerror(0) == b"ok"
     assert b"invalid" in lib.mppi_strerror(-1)
     assert b"terrain" in lib.mppi_strerror(-3)

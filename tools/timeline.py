@@ -20,8 +20,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-PHASES = ["entry", "setup_done", "rollout_start", "rollout_end", "roles_joined", "partial_published", "update_done", "smid",
-          "cost_ready", "block_min", "block_sum_compact", "ticket", "g_min", "g_fold", "g_nominal", "g_cmd"] + ["smid"] * 16
 NS = 32
 
 
@@ -81,33 +79,56 @@ def main():
         clk_rows.append(t.copy())
     if a.dump:
         np.save(a.dump, np.stack(raw_rows))
-    rel = np.stack(rows)                                  # [reps, nblocks, 7]
-    out = {"workload": w.name, "K": w.K, "T": w.T, "math": a.math, "variant": a.variant, "nblocks": int(nb.value),
+    rel_all = np.stack(rows)                              # [reps, grid.x, 32]
+    pipe = bool(np.isfinite(rel_all[:, -1, 12]).all() and not np.isfinite(rel_all[:, -1, 3]).any())
+    # pipelined kernel (LL protocol): the last row is the UPDATER block, the others are worker blocks
+    rel = rel_all[:, :-1] if pipe else rel_all
+    out = {"workload": w.name, "K": w.K, "T": w.T, "math": a.math, "variant": a.variant,
+           "nblocks": int(rel.shape[1]), "updater_block": pipe,
            "event_us": {"median": float(np.median(evt)), "min": float(np.min(evt))},
            "sms_used": int(len(np.unique(trace[:, 7].cpu().numpy()))), "phases_us": {}}
     import warnings
     warnings.simplefilter("ignore")
-    for j, name in enumerate(PHASES):
-        if name == "smid":
-            continue
+    worker_phases = {0: "entry", 1: "setup_done", 2: "rollout_start", 3: "rollout_end", 4: "roles_joined", 8: "cost_ready",
+                     5: "header_published" if pipe else "partial_published", 10: "block_softmax_done",
+                     11: "rows_published" if pipe else "ticket"}
+    for j, name in worker_phases.items():
         x = rel[:, :, j]
         out["phases_us"][name] = {"first": float(np.nanmedian(np.nanmin(x, axis=1))),
                                   "median": float(np.nanmedian(x)),
                                   "last": float(np.nanmedian(np.nanmax(x, axis=1)))}
-    # SM-clock stamps of the last block's update (cycles since its ticket was requested)
-    raw = np.stack(clk_rows)                              # [reps, nblocks, 32]
-    cyc = {}
-    names = {23: "ticket_known", 16: "enter_update", 17: "min_done", 18: "scales_compacted", 19: "fold_done",
-             20: "nominal_done", 21: "recurrence_done", 22: "outputs_done"}
-    for slot, name in names.items():
-        vals = []
-        for r in range(raw.shape[0]):
-            b = int(np.argmax(raw[r, :, 22]))             # the block that ran the update
-            if raw[r, b, 22] > 0 and raw[r, b, slot] > 0:
-                vals.append(raw[r, b, slot] - raw[r, b, 24])
-        if vals:
-            cyc[name] = float(np.median(vals))
-    out["last_block_update_cycles"] = cyc
+    if pipe:
+        upd = rel_all[:, -1]
+        for j, name in {0: "entry", 1: "poll_start", 2: "headers_complete", 12: "g_min", 13: "g_fold", 14: "g_nominal",
+                        15: "g_cmd", 6: "update_done"}.items():
+            out["phases_us"]["updater_" + name] = float(np.nanmedian(upd[:, j]))
+        out["tail_us"] = {
+            "last_header_published_to_headers_complete": float(np.nanmedian(upd[:, 2] - np.nanmax(rel[:, :, 5], axis=1))),
+            "headers_complete_to_command": float(np.nanmedian(upd[:, 15] - upd[:, 2])),
+            "command_to_update_done": float(np.nanmedian(upd[:, 6] - upd[:, 15])),
+            "last_rollout_end_to_update_done": float(np.nanmedian(upd[:, 6] - np.nanmax(rel[:, :, 3], axis=1)))}
+        rawu = np.stack(clk_rows)[:, -1]                      # SM-clock stamps of the updater's real pass
+        names = {17: "own_headers", 18: "block_min", 19: "scales_compacted", 20: "S_sums", 21: "fold_loaded",
+                 22: "fold_barrier", 23: "nominal", 24: "command_stats", 26: "recurrence(warp1)", 27: "recurrence_barrier",
+                 28: "outputs"}
+        out["updater_cycles_since_poll_start"] = {nm: float(np.median(rawu[:, sl] - rawu[:, 16])) for sl, nm in names.items()}
+    else:
+        for j, name in {12: "g_min", 13: "g_fold", 14: "g_nominal", 15: "g_cmd", 6: "update_done"}.items():
+            out["phases_us"][name] = float(np.nanmedian(np.nanmax(rel[:, :, j], axis=1)))
+        # SM-clock stamps of the last block's update (cycles since its ticket was requested)
+        raw = np.stack(clk_rows)                              # [reps, nblocks, 32]
+        cyc = {}
+        names = {23: "ticket_known", 16: "enter_update", 17: "min_done", 18: "scales_compacted", 19: "fold_done",
+                 20: "nominal_done", 21: "recurrence_done", 22: "outputs_done"}
+        for slot, name in names.items():
+            vals = []
+            for r in range(raw.shape[0]):
+                b = int(np.argmax(raw[r, :, 22]))             # the block that ran the update
+                if raw[r, b, 22] > 0 and raw[r, b, slot] > 0:
+                    vals.append(raw[r, b, slot] - raw[r, b, 24])
+            if vals:
+                cyc[name] = float(np.median(vals))
+        out["last_block_update_cycles"] = cyc
     x = rel[:, :, 25] - rel[:, :, 2]
     out["phases_us"]["tile_landed_after_rollout_start"] = {"min": float(np.nanmin(x)), "median": float(np.nanmedian(x)),
                                                            "max": float(np.nanmax(x))}

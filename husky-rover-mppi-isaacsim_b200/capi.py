@@ -99,6 +99,7 @@ SYMBOLS = {
     "mppi_run_closed_loop": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64,
                                        C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
+    "mppi_closed_loop_last_input": (C.c_int, [_H, C.POINTER(MppiState)]),
     "mppi_sim_rollout": (C.c_int, [_H, C.POINTER(MppiState), C.c_void_p]),
     "mppi_debug_dump": (C.c_int, [_H, C.POINTER(MppiState), C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32,
                                   C.POINTER(MppiDebugDump), C.c_void_p]),

@@ -35,14 +35,42 @@ class Surface:
         self.Z = np.zeros((grid_size, grid_size), dtype=np.float32)
         self.costmap = np.zeros((self.costmap_size, self.costmap_size), dtype=np.float32)
         self.obstacles = obstacles
+        self._grids = {}
         if which_map == "manual":
             self.Z = self.create_surface(bumps)
-        elif which_map == "imported":
-            self.Z = np.load(filename)
+        if which_map == "imported":
+            _, _, self.Z = self.import_surface(filename, 1000, 2500, bumps)      # MPPI_isaac.py:285-288
         if which_costmap == "manual":
             self.costmap = self.create_obstacles_costmap(obstacles, origin)
-        if which_map == "imported" and costmap_file:
-            self.costmap = np.load(costmap_file)
+        if which_map == "imported":                                              # MPPI_isaac.py:296-297 (unconditional)
+            self.costmap = self.import_obstacles_costmap(costmap_file)
+
+    # The reference builds four full meshgrids in its constructor (MPPI_isaac.py:267-277: X, Y over the DEM grid,
+    # X_costmap, Y_costmap over the costmap grid; 7000^2 float64 x 2 = 784 MB at the Isaac sizes).  Only its plotting
+    # helpers read them, so here they are built on first access.
+    def _grid(self, name):
+        if name not in self._grids:
+            n = self.grid_size if name in ("X", "Y") else self.costmap_size
+            ax = np.linspace(-self.half_width, self.half_width, n)
+            gx, gy = np.meshgrid(ax, ax)
+            self._grids["X" if name in ("X", "Y") else "X_costmap"] = gx
+            self._grids["Y" if name in ("X", "Y") else "Y_costmap"] = gy
+        return self._grids[name]
+
+    X = property(lambda self: self._grid("X"))
+    Y = property(lambda self: self._grid("Y"))
+    X_costmap = property(lambda self: self._grid("X_costmap"))
+    Y_costmap = property(lambda self: self._grid("Y_costmap"))
+
+    def import_surface(self, filename, start_index, end_index, bumps):
+        """MPPI_isaac.py:301-307: returns (X, Y, Z) with Z loaded from `filename` (X, Y span end - start samples)."""
+        ax = np.linspace(-self.half_width, self.half_width, end_index - start_index)
+        X, Y = np.meshgrid(ax, ax)
+        return X, Y, np.load(filename)
+
+    def import_obstacles_costmap(self, costmap_file):
+        """MPPI_isaac.py:358-359."""
+        return np.load(costmap_file)
 
     def create_surface(self, bumps) -> np.ndarray:
         """Crater field: sum of (h-0.5) exp(-r^2/2w^2) - (h+0.5) exp(-r^2/2(w/2)^2), MPPI_isaac.py:317-320."""
@@ -447,7 +475,15 @@ class MPPI_Controller:
             self.robot.ang_vel.append(row[7])
         self.std_dev_u1, self.std_dev_u2 = np.float32(st.sigma1), np.float32(st.sigma2)
         self.robot.left_wheel_speed, self.robot.right_wheel_speed = np.float32(st.wheel_l), np.float32(st.wheel_r)
-        self._last_state, self._last_proj = st, pj
+        # replays (.trajectories, debug_dump, visualiser_points) must show the fan of rollouts the LAST executed
+        # iteration really sampled: its input state and its offset, not the state after its plant step
+        if k > 0:
+            last_in = capi.MppiState()
+            capi.check(self._lib.mppi_closed_loop_last_input(self._handle, C.byref(last_in)),
+                       "mppi_closed_loop_last_input")
+            self._last_state, self._last_proj, self._last_offset = last_in, pj, self._step_count + k - 1
+            if noise is not None:
+                self._injected_noise = noise[k - 1]
         self._step_count += k
         self.loop += k
         self._sim_stale = True

@@ -4,6 +4,7 @@
 #include "mppi_kernels.cuh"
 
 #include <cuda.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdio>
 #include <cmath>
@@ -49,7 +50,9 @@ struct MppiHandle {
     PeerComm peers;
     int comm_nblocks;            // blocks per rank the exchange buffers were laid out for
     // device-resident closed loop (mppi_run_closed_loop)
-    MppiState* loop_state;       // device
+    MppiState* loop_state;       // device: [0] the loop's state, [1] the state the last executed iteration sampled from
+    MppiState loop_last_input;   // host copy of [1] after mppi_run_closed_loop
+    bool loop_last_input_valid;
     int32_t* loop_ctl;           // device {iterations done, goal reached}
     float* loop_log;             // device [loop_log_cap][8]
     int32_t loop_log_cap;
@@ -374,11 +377,14 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
         }
     }
     if (h->timing) CK(cudaEventRecord(h->ev0, s));
+    // NVTX range around the launch (a no-op without a profiler attached): mppi_step [pipe | mono]
+    nvtxRangePushA(h->pipe ? "mppi_step [pipelined kernel]" : "mppi_step [monolithic kernel]");
     cudaError_t e;
     if (h->pipe)
         e = MPPI_BY_NS(h->p, launch_fused_pipe(a, proj, n_rovers, s));
     else
         e = MPPI_BY_NS(h->p, launch_fused(a, proj, n_rovers, h->block, s));
+    nvtxRangePop();
     if (e != cudaSuccess) return cuda_fail(e, "launch_fused");
     if (h->timing) { CK(cudaEventRecord(h->ev1, s)); h->timed_valid = true; }
     return MPPI_OK;
@@ -506,6 +512,7 @@ extern "C" int mppi_comm_connect(MppiHandle* h, int32_t rank, int32_t world, con
     h->peers.world = world;
     h->peers.nblocks = h->comm_nblocks;
     h->peers.seq = 0;
+    h->peers.pull = getenv("MPPI_EXCHANGE_PULL") ? atoi(getenv("MPPI_EXCHANGE_PULL")) : 0;
     return MPPI_OK;
 }
 
@@ -542,7 +549,7 @@ extern "C" int mppi_run_closed_loop(MppiHandle* h, MppiState* state_inout, int32
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaSetDevice(h->device));
     if (!h->loop_state) {
-        CK(cudaMalloc((void**)&h->loop_state, sizeof(MppiState)));
+        CK(cudaMalloc((void**)&h->loop_state, 2 * sizeof(MppiState)));
         CK(cudaMalloc((void**)&h->loop_ctl, 2 * sizeof(int32_t)));
     }
     if (log_host && h->loop_log_cap < max_iters) {
@@ -555,7 +562,7 @@ extern "C" int mppi_run_closed_loop(MppiHandle* h, MppiState* state_inout, int32
     CK(cudaMemsetAsync(h->loop_ctl, 0, 2 * sizeof(int32_t), s));
     LoopCtl lc;
     memset(&lc, 0, sizeof(lc));
-    lc.state = h->loop_state; lc.ctl = h->loop_ctl; lc.log = log_host ? h->loop_log : nullptr;
+    lc.state = h->loop_state; lc.prev_state = h->loop_state + 1; lc.ctl = h->loop_ctl; lc.log = log_host ? h->loop_log : nullptr;
     lc.goal_tol = goal_tol; lc.sigma_base = sigma_base; lc.sigma_gain = sigma_gain;
     // Launches are enqueued back to back; a launch that finds the goal flag set returns at once.  The host looks at
     // the flag every `kCheck` iterations only, so the device never waits for it.
@@ -574,12 +581,22 @@ extern "C" int mppi_run_closed_loop(MppiHandle* h, MppiState* state_inout, int32
         }
     }
     CK(cudaMemcpyAsync(ctl, h->loop_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
+    h->loop_last_input = *state_inout;                           // stands when no iteration runs
     CK(cudaMemcpyAsync(state_inout, h->loop_state, sizeof(MppiState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (ctl[0] > 0) CK(cudaMemcpy(&h->loop_last_input, h->loop_state + 1, sizeof(MppiState), cudaMemcpyDeviceToHost));
+    h->loop_last_input_valid = true;
     if (log_host && ctl[0] > 0)
         CK(cudaMemcpy(log_host, h->loop_log, (size_t)ctl[0] * 8 * sizeof(float), cudaMemcpyDeviceToHost));
     if (iters_done) *iters_done = ctl[0];
     if (goal_reached) *goal_reached = ctl[1];
+    return MPPI_OK;
+}
+
+extern "C" int mppi_closed_loop_last_input(MppiHandle* h, MppiState* state_out)
+{
+    if (!h || !state_out || !h->loop_last_input_valid) return MPPI_ERR_INVALID_ARG;
+    *state_out = h->loop_last_input;
     return MPPI_OK;
 }
 

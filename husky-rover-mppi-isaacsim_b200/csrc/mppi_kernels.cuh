@@ -49,6 +49,9 @@ struct PeerComm {
     int32_t rank, world;              // world == 0: no peer exchange
     int32_t nblocks;                  // blocks per rank the buffers were laid out for
     uint32_t seq;                     // step sequence number (parity = seq & 1 selects the buffer half)
+    int32_t pull;                     // flat variant: 0 = every worker block PUSHES its lines into every rank's buffer;
+                                      // 1 = it stores them into its own rank's buffer only and the updaters PULL (poll
+                                      // the other ranks' buffers over NVLink): no peer writes at all
 };
 
 // Device-resident closed loop (mppi_run_closed_loop): the plant of MPPI_Controller.run (MPPI_isaac.py:755-805) is the
@@ -58,6 +61,7 @@ struct PeerComm {
 // the next iteration's state -- one launch per control iteration, no host round trip.
 struct LoopCtl {
     MppiState* state;                 // device, in/out; nullptr: loop mode off
+    MppiState* prev_state;            // device, out: the state the LAST executed iteration sampled from (for replays)
     float* log;                       // device [max_iters][8] {x, y, z, hx, hy, hz, v*, w*} after each iteration, or nullptr
     int32_t* ctl;                     // device {iterations done, goal reached}
     float goal_tol;                   // stop when |x - goal_x| <= tol and |y - goal_y| <= tol   (0.5, MPPI_isaac.py:763)

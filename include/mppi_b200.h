@@ -235,6 +235,11 @@ int mppi_run_closed_loop(MppiHandle *h, MppiState *state_inout, int32_t proj, co
                          uint64_t seed, uint64_t offset0, int32_t max_iters, float goal_tol, float sigma_base,
                          float sigma_gain, float *log_host, int32_t *iters_done, int32_t *goal_reached, void *stream);
 
+/* The state the LAST executed iteration of mppi_run_closed_loop sampled from (its pose, sigmas and wheel speeds BEFORE
+ * that iteration's plant step): together with (seed, offset0 + iterations - 1) it replays that iteration's fan of
+ * rollouts through mppi_debug_dump / mppi_export_trajectories, as MPPI_step's own bookkeeping does for a single step. */
+int mppi_closed_loop_last_input(MppiHandle *h, MppiState *state_out);
+
 /* Validation / visualiser path: re-runs sampling + rollout + critics for rover 0 and writes the requested
  * K x T intermediates (what the unfused reference keeps in `trajectories`, `left_wheel_pos`, ...). Uses the
  * nominal sequence as it was BEFORE the last step when `use_previous_nominal` != 0. */

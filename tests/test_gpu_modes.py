@@ -218,6 +218,65 @@ def test_controller_run_closed_loop_reaches_a_near_goal():
     ctl.close()
 
 
+def test_device_loop_replays_the_fan_of_its_last_iteration():
+    """After run(device_loop=True) the replay views (.trajectories, visualiser_points, debug_dump) must show the
+    rollouts the LAST executed iteration sampled -- its input state and its noise offset -- exactly as after the
+    host-driven loop (round-1 advisor finding: the device loop left a stale offset and the post-step state)."""
+    import mppi_b200
+    from mppi_b200 import MPPI_Controller, Robot, Surface
+    dem, cm, hw = terrain("small")
+
+    def make():
+        surface = Surface("", "", "", "", grid_size=256, half_width=12.8, origin=(0, 0), bumps=[], radius_robot=0.3)
+        surface.Z = dem
+        surface.costmap_size, surface.costmap_resolution, surface.costmap = 128, 25.6 / 128, cm
+        robot = Robot(x=-6.0, y=-6.0, heading_vector=[1.0, 1.0, 0.0], config_file=mppi_b200.DEFAULT_CONFIG)
+        return robot, MPPI_Controller(surface, robot, mppi_b200.DEFAULT_CONFIG, goal_x=4.0, goal_y=5.0,
+                                      goal_orientation=0.0,
+                                      overrides=dict(number_of_trajectories=512, number_of_iterations=40))
+
+    rh, ch = make()
+    ch.run("3d", max_loops=5)
+    rd, cd = make()
+    cd.run("3d", max_loops=5, device_loop=True)
+    assert ch.loop == cd.loop == 5
+    assert np.array_equal(np.asarray(rh.x, np.float32), np.asarray(rd.x, np.float32))
+    th, td = ch.trajectories.numpy(), cd.trajectories.numpy()
+    assert np.array_equal(th, td)                                     # same fan of rollouts, bit for bit
+    assert np.array_equal(th[0::40][:, :2], td[0::40][:, :2])
+    # ... and it IS the last iteration's fan: every rollout starts one step away from the pose BEFORE the last plant step
+    start = np.array([rd.x[-2], rd.y[-2]], np.float32)
+    first = td.reshape(512, 40, 3)[:, 0, :2]
+    assert np.all(np.linalg.norm(first - start, axis=1) <= 2.0 * 0.045 + 1e-4)
+    ph, _ = ch.visualiser_points(0.0, 0.0, 0.0)
+    pd, _ = cd.visualiser_points(0.0, 0.0, 0.0)
+    assert np.array_equal(ph, pd)
+    ch.close()
+    cd.close()
+
+
+def test_two_handles_on_two_devices_in_one_process():
+    """The 227 KB dynamic shared-memory opt-in is per (device, kernel): a second handle on another GPU of the same
+    process must run the pipelined kernel with its 144 KB DEM tile too (round-1 advisor finding).  Needs 2 GPUs."""
+    import torch
+    from mppi_b200.core import Core, make_state
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    dem, cm, hw = terrain("C1")
+    st = make_state(-60.57, -60.23, goal_x=65.8, goal_y=65.4)
+    res = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        core = Core(4096, 100, device=d)
+        core.set_terrain(torch.from_numpy(dem).to(dev), hw, torch.from_numpy(cm).to(dev))
+        with torch.cuda.device(d):
+            core.step(st, seed=42, offset=3, stream=torch.cuda.current_stream(dev))
+            torch.cuda.synchronize(dev)
+        res.append((core.optimal_u1[0].cpu().numpy().copy(), core.read_stats()))
+        core.close()
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1]["argmin"] == res[1][1]["argmin"]
+
+
 def test_fused_peer_exchange_world1_equals_plain_step(oracle):
     """The sample-sharded step with the exchange fused into the launch (mppi_step_sharded), world = 1: the rank
     partial goes through the exchange buffer and the flag hand-shake and must reproduce mppi_step."""

@@ -23,6 +23,70 @@ sys.path.insert(0, ROOT)
 NS = 32
 
 
+def sharded(a):
+    """Per-rank timeline of the sharded step.  %globaltimer is per GPU, so only differences WITHIN a rank are reported:
+    how long the rank's updater waits after its own last worker has published (= remote blocks that finish later +
+    NVLink flight + polling), and what it costs afterwards."""
+    import torch
+    import torch.distributed as dist
+    from mppi_b200 import capi, synthetic as syn
+    from mppi_b200.core import Core, make_state
+    from mppi_b200.sharding import SampleShardedStepper
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    w = syn.WORKLOADS[a.workload]
+    if a.K or a.T:
+        w = dataclasses.replace(w, K=a.K or w.K, T=a.T or w.T)
+    dem = syn.crater_dem(w.grid_size, w.half_width).to(dev)
+    cm = torch.from_numpy(syn.rock_costmap(w.costmap_size, w.half_width)).to(dev)
+    start, goal = syn.workload_start_goal(w)
+    core = Core(w.K, w.T, device=local, math=a.math)
+    core.set_terrain(dem, w.half_width, cm)
+    st = make_state(start[0], start[1], goal_x=goal[0], goal_y=goal[1])
+    stepper = SampleShardedStepper(core, w.K * world, transport="p2p")
+    nb = C.c_int32()
+    capi.check(core.L.mppi_set_trace(core.h, None, C.byref(nb)), "mppi_set_trace")
+    trace = torch.zeros((nb.value, NS), dtype=torch.int64, device=dev)
+    capi.check(core.L.mppi_set_trace(core.h, trace.data_ptr(), None), "mppi_set_trace")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows, evt = [], []
+    for rep in range(a.reps):
+        dist.barrier()
+        for j in range(8):
+            if not a.no_flush:
+                flush.fill_(j)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            stepper.step(st, capi.PROJ_3D, 42, 1000 * rep + j)
+            e1.record()
+        torch.cuda.synchronize()
+        evt.append(e0.elapsed_time(e1) * 1e3)
+        t = trace.cpu().numpy().astype(np.float64)
+        rel = (t - t[:, 0].min()) / 1e3
+        rel[t == 0] = np.nan
+        rows.append(rel)
+    rel = np.stack(rows)
+    wk, upd = rel[:, :-1], rel[:, -1]
+    med = lambda x: float(np.nanmedian(x))                                        # noqa: E731
+    out = {"rank": rank, "world": world, "event_us_last_of_8": med(evt),
+           "rollout_end_last": med(np.nanmax(wk[:, :, 3], axis=1)),
+           "own_last_header_published": med(np.nanmax(wk[:, :, 5], axis=1)),
+           "updater_all_headers_and_min": med(upd[:, 12]), "updater_fold": med(upd[:, 13]),
+           "updater_command": med(upd[:, 15]), "updater_done": med(upd[:, 6]),
+           "wait_after_own_last_header": med(upd[:, 12] - np.nanmax(wk[:, :, 5], axis=1)),
+           "headers_to_command": med(upd[:, 15] - upd[:, 12]), "command_to_done": med(upd[:, 6] - upd[:, 15])}
+    every = [None] * world
+    dist.all_gather_object(every, out)
+    if rank == 0:
+        print(json.dumps({"workload": w.name, "K_per_gpu": w.K, "T": w.T, "world": world, "l2_flushed": not a.no_flush,
+                          "ranks": every}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="C2")
@@ -33,7 +97,12 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between launches")
     ap.add_argument("--dump", default="", help="save the per-block stamps of every repetition as .npy [reps, nblocks, 8]")
+    ap.add_argument("--sharded", action="store_true",
+                    help="run under torchrun: the sample-sharded step (fused NVLink exchange), one summary per rank; the "
+                         "traced launch is the last of 8 back-to-back steps, so the ranks are in their steady-state lock step")
     a = ap.parse_args()
+    if a.sharded:
+        return sharded(a)
 
     import torch
     from mppi_b200 import capi, synthetic as syn

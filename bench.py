@@ -157,7 +157,7 @@ EXT_CRITICS = dict(cw_slope_path=50.5, cw_roll=400.0, cw_pitch=250.0)
 
 def critic_weights(args):
     """Optional critic weights of this run (see --critics)."""
-    ext = args.critics == "ext" or (args.critics == "auto" and args.workload == "C5")
+    ext = args.critics == "ext" or (args.critics == "auto" and args.workload in ("C5", "C5many"))
     return dict(EXT_CRITICS) if ext else {}
 
 
@@ -490,30 +490,58 @@ def run_c3(ctx, args):
     return out
 
 
-def run_c4(ctx, args, K=0, T=0):
+def many_start_states(w, n_side=8):
+    """C5many: n_side^2 poses on a grid spread over the map, headings fanned out, goals mirrored through the centre."""
+    from mppi_b200.core import make_state
+    span = w.half_width * 0.75
+    xs = np.linspace(-span, span, n_side)
+    states = []
+    for j, y in enumerate(xs):
+        for i, x in enumerate(xs):
+            a = 2 * np.pi * ((i * n_side + j) % 16) / 16.0
+            states.append(make_state(float(x), float(y), (float(np.cos(a)), float(np.sin(a)), 0.0),
+                                     goal_x=float(-x), goal_y=float(-y)))
+    return states
+
+
+def run_c4(ctx, args, K=0, T=0, many=False):
     """BASELINE config 4: independent controllers sharded by rover, no communication.  Each GPU runs `--rovers`
     rovers (default 512 = 4096 / 8) x K = 1024 x T = 64 in ONE launch (grid.y = rover); every rover has its own DEM /
-    costmap memory, pose, goal, nominal and Philox stream.  Returns the measurement as a dict."""
+    costmap memory, pose, goal, nominal and Philox stream.  Returns the measurement as a dict.
+
+    many=True (--workload C5many): BASELINE config 5's 8192^2 DEM (268 MB) with 64 controllers x K = 1024 x T = 200
+    started on an 8 x 8 grid of poses over ONE shared map: the touched windows add up to ~530 MB, so -- unlike the
+    single-start C5, whose 8 MB window stays in L2 -- the terrain gathers really come from HBM."""
     import torch
     from mppi_b200 import capi, synthetic as syn
     from mppi_b200.core import Core, make_state
     dev, world, rank = ctx.dev, ctx.world, ctx.rank
-    w = syn.WORKLOADS["C4"]
-    K, T, R = K or w.K, T or w.T, args.rovers
-    pool = 16                                        # distinct synthetic maps; every rover gets its OWN copy in HBM
-    rng = np.random.default_rng(7 + rank)
-    dem_pool = torch.stack([syn.crater_dem(w.grid_size, w.half_width, seed=57 + i, device=dev) for i in range(pool)])
-    cm_pool = torch.stack([torch.from_numpy(syn.rock_costmap(w.costmap_size, w.half_width, n_rocks=90, seed=99 + i))
-                           for i in range(pool)]).to(dev)
-    idx = torch.arange(R, device=dev) % pool
-    dems, cms = dem_pool[idx].contiguous(), cm_pool[idx].contiguous()
-    core = Core(K, T, device=ctx.local_rank, math=args.math, max_rovers=R)
-    core.set_terrain_batched(dems, w.half_width, cms)
-    half = w.half_width / 2
-    states = [make_state(float(rng.uniform(-half, half)), float(rng.uniform(-half, half)),
-                         (float(np.cos(a)), float(np.sin(a)), 0.0), goal_x=float(rng.uniform(-half, half)),
-                         goal_y=float(rng.uniform(-half, half)))
-              for a in rng.uniform(0, 2 * np.pi, R)]
+    w = syn.WORKLOADS["C5" if many else "C4"]
+    if many:
+        states = many_start_states(w)
+        K, T, R = K or 1024, T or w.T, len(states)
+        pool = 1
+        dem = syn.crater_dem(w.grid_size, w.half_width, device=dev).contiguous()
+        cm = torch.from_numpy(syn.rock_costmap(w.costmap_size, w.half_width)).to(dev)
+        dems, cms = dem.unsqueeze(0).expand(R, -1, -1), cm.unsqueeze(0).expand(R, -1, -1)
+        core = Core(K, T, device=ctx.local_rank, math=args.math, max_rovers=R, **critic_weights(args))
+        core.set_terrain_batched_shared(dems, w.half_width, cms)
+    else:
+        K, T, R = K or w.K, T or w.T, args.rovers
+        pool = 16                                    # distinct synthetic maps; every rover gets its OWN copy in HBM
+        rng = np.random.default_rng(7 + rank)
+        dem_pool = torch.stack([syn.crater_dem(w.grid_size, w.half_width, seed=57 + i, device=dev) for i in range(pool)])
+        cm_pool = torch.stack([torch.from_numpy(syn.rock_costmap(w.costmap_size, w.half_width, n_rocks=90, seed=99 + i))
+                               for i in range(pool)]).to(dev)
+        idx = torch.arange(R, device=dev) % pool
+        dems, cms = dem_pool[idx].contiguous(), cm_pool[idx].contiguous()
+        core = Core(K, T, device=ctx.local_rank, math=args.math, max_rovers=R)
+        core.set_terrain_batched(dems, w.half_width, cms)
+        half = w.half_width / 2
+        states = [make_state(float(rng.uniform(-half, half)), float(rng.uniform(-half, half)),
+                             (float(np.cos(a)), float(np.sin(a)), 0.0), goal_x=float(rng.uniform(-half, half)),
+                             goal_y=float(rng.uniform(-half, half)))
+                  for a in rng.uniform(0, 2 * np.pi, R)]
     states_host = torch.frombuffer(bytearray(bytes((capi.MppiState * R)(*states))), dtype=torch.uint8).pin_memory()
     states_dev = states_host.to(dev)
     cmd_host = torch.empty((R, 2), dtype=torch.float32).pin_memory()
@@ -521,7 +549,7 @@ def run_c4(ctx, args, K=0, T=0):
     def one(i):
         core.step_batched(states_dev, R, capi.PROJ_3D, 42, i)
 
-    steps = min(args.steps if args.workload == "C4" else args.extras_steps, 100)
+    steps = min(args.steps if args.workload in ("C4", "C5many") else args.extras_steps, 100)
     warm = max(3, min(args.warmup, 10))
     ctx.timed_loop(one, warm, 0, ctx.do_flush)
     sampler = ClockSampler(ctx.local_rank)
@@ -552,8 +580,8 @@ def run_c4(ctx, args, K=0, T=0):
     torch.cuda.synchronize(dev)
     costs_b = core.costs[0].cpu().numpy().copy()
     u1_b = core.optimal_u1[0].cpu().numpy().copy()
-    solo = Core(K, T, device=ctx.local_rank, math=args.math)
-    solo.set_terrain(dems[0], w.half_width, cms[0])
+    solo = Core(K, T, device=ctx.local_rank, math=args.math, **(critic_weights(args) if many else {}))
+    solo.set_terrain(dems[0].contiguous() if not many else dem, w.half_width, cms[0].contiguous() if not many else cm)
     solo.step(states[0], capi.PROJ_3D, None, 42, 77)
     torch.cuda.synchronize(dev)
     check = {"rover0_costs_bitwise": bool(np.array_equal(costs_b, solo.costs[0].cpu().numpy())),
@@ -564,10 +592,11 @@ def run_c4(ctx, args, K=0, T=0):
     solo.close()
     units = R * K * T
     dur = ms * 1e-3
-    res = {"workload": w.name, "rovers_per_gpu": R, "rovers_total": R * world, "K": K, "T": T, "steps": steps, "warmup": warm,
+    res = {"workload": (w.name + " [64 starts x K=1024 on ONE shared DEM]") if many else w.name, "rovers_per_gpu": R, "rovers_total": R * world, "K": K, "T": T, "steps": steps, "warmup": warm,
            "ms_per_step": ms, "value": units * world / dur, "unit": "sample-steps/s", "rover_updates_per_s": R * world / dur,
            "p50_us": float(np.median(per) * 1e3), "p99_us": float(np.percentile(per, 99) * 1e3),
-           "dem": f"{w.grid_size}x{w.grid_size} f32 per rover ({pool} distinct maps, one copy per rover)",
+           "dem": (f"{w.grid_size}x{w.grid_size} f32, ONE map shared by all starts" if many else
+                   f"{w.grid_size}x{w.grid_size} f32 per rover ({pool} distinct maps, one copy per rover)"),
            "costmap": f"{w.costmap_size}x{w.costmap_size} f32 per rover", "math": args.math,
            "parallelism": f"rover-sharded x{world}, no communication",
            "e2e": {"value": units * world / e2e_mean, "unit": "sample-steps/s", "h2d_bytes_per_step": R * STATE_BYTES,
@@ -579,8 +608,9 @@ def run_c4(ctx, args, K=0, T=0):
 
 
 def run_rover_batch_line(ctx, args):
-    """--workload C4: the rover-sharded batch as the top-level line."""
-    r = run_c4(ctx, args, args.K, args.T)
+    """--workload C4 / C5many: the rover-sharded batch as the top-level line."""
+    many = args.workload == "C5many"
+    r = run_c4(ctx, args, args.K, args.T, many=many)
     if ctx.rank == 0:
         pk = peaks()
         lp = live_peaks(ctx.local_rank)
@@ -595,8 +625,10 @@ def run_rover_batch_line(ctx, args):
                       {"l2": "flushed between timed iterations (256 MiB fill)" if ctx.do_flush else "warm"},
             "latency_us": {"p50": r["p50_us"], "p99": r["p99_us"]},
             "rover_updates_per_s": r["rover_updates_per_s"], "e2e": r["e2e"], "gpu_launches": r["steps"],
-            "roofline": roofline_object("mono", units, r["T"], dur, pk, lp, {}, 1.0,
-                                        "mppi_fused_kernel<3D, Philox>, grid.y = rover"),
+            "roofline": roofline_object("mono", units, r["T"], dur, pk, lp,
+                                        kernel_counters("C5many" if many else "C4", args.math, r["K"], r["T"], "mono")
+                                        if ctx.world == 1 and r["rovers_per_gpu"] == (64 if many else 512) else {},
+                                        None, "mppi_fused_kernel<3D, Philox>, grid.y = rover"),
             "check": r["check"], "clocks": r["clocks"], "stats_rover0": r["stats_rover0"],
         }
         emit(line)
@@ -634,6 +666,17 @@ def roofline_object(kernel_kind, units, T, dur_s, pk, lp, counters, share, kerne
                       "peak_source": "measured live (random 32-byte-sector gathers from L2)",
                       "note": "upper bound of what the lookups would cost if none were staged in shared memory / L1"},
     }
+    if counters.get("dram_bytes_per_launch"):
+        t = counters["dram_bytes_per_launch"] / dur_s / 1e9
+        r["hbm_measured"] = {"achieved": t, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": t / pk["hbm_gbs"],
+                             "note": "DRAM bytes per launch from the committed ncu capture of THIS configuration "
+                                     "(dram__bytes_read + write) over the launch time measured here"}
+    if counters.get("l2_sectors_per_launch") and not counters.get("extrapolated"):
+        g = counters["l2_sectors_per_launch"] * 32.0 / dur_s / 1e9
+        r["l2_measured"] = {"achieved": g, "peak": lp["l2_gather_gbs"], "unit": "GB/s", "frac": g / lp["l2_gather_gbs"],
+                            "hit_rate_pct": counters.get("l2_hit_pct"),
+                            "note": "lts__t_sectors x 32 B per launch (ncu capture of this configuration) over the launch "
+                                    "time measured here, against the live L2 random-gather rate"}
     if kernel_kind == "pipe":
         r["latency"] = {"ns_per_horizon_step": dur_s * 1e9 / T, "unit": "ns",
                         "note": "the whole launch divided by T: the chain warp's dependent issue latency per horizon step "
@@ -676,7 +719,7 @@ def main():
     from mppi_b200.core import make_state
 
     ctx = Ctx(args)
-    if args.workload == "C4":
+    if args.workload in ("C4", "C5many"):
         run_rover_batch_line(ctx, args)
         ctx.close()
         return

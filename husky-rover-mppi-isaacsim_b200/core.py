@@ -81,6 +81,18 @@ class Core:
         self._keep["terrains"] = (dems, costmaps, raw)
         capi.check(self.L.mppi_set_terrain_batched(self.h, raw.data_ptr(), R), "mppi_set_terrain_batched")
 
+    def set_terrain_batched_shared(self, dems: torch.Tensor, half_width: float, costmaps: torch.Tensor):
+        """Batched controllers over ONE shared map: dems / costmaps are [R, gs, gs] / [R, cms, cms] VIEWS (expanded,
+        stride 0 over rovers) of a single DEM / costmap -- every rover's MppiTerrain points at the same memory."""
+        R, gs, cms = dems.shape[0], dems.shape[1], costmaps.shape[1]
+        arr = (capi.MppiTerrain * R)()
+        for r in range(R):
+            arr[r] = capi.MppiTerrain(dems[r].data_ptr(), gs, half_width, 2.0 * half_width / gs,
+                                      costmaps[r].data_ptr(), cms, 2.0 * half_width / cms)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        self._keep["terrains"] = (dems, costmaps, raw)
+        capi.check(self.L.mppi_set_terrain_batched(self.h, raw.data_ptr(), R), "mppi_set_terrain_batched")
+
     @staticmethod
     def pack_states(states, device) -> torch.Tensor:
         arr = (capi.MppiState * len(states))(*states)

@@ -1478,6 +1478,11 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     float* nominal2 = A.nominal2 + (size_t)rover * T;
     // (the updater block's code is placed AFTER the workers' -- see the end of the kernel)
     if (__builtin_expect(!is_updater, 1)) {
+#ifdef MPPI_AB_PAD
+    // A/B knob: shifts every following instruction of the workers' code by 16 x MPPI_AB_PAD bytes (layout probe)
+#pragma unroll
+    for (int pad_i = 0; pad_i < MPPI_AB_PAD; ++pad_i) asm volatile("nanosleep.u32 0;");
+#endif
     if (tid == 0) {
         for (int i = 0; i < kPipeStages; ++i) {
             mbar_init(&ps.full_u[i], 32); mbar_init(&ps.empty_u[i], 32);
@@ -1715,7 +1720,10 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     }   // !dry: roles
 
     // ---- tail part 1: cost, block partial, header lines (one warp; see pipe_header for the dry trip)
-    if (role == (dry ? ROLE_OBST : ROLE_NOISE0)) pipe_header(A, st, sc, s, ps, rover, lane, valid, snap, dry);
+#ifndef MPPI_DRY_ROLE
+#define MPPI_DRY_ROLE ROLE_OBST            // A/B knob: which idle warp runs the warm-up trip (measured: no difference)
+#endif
+    if (role == (dry ? MPPI_DRY_ROLE : ROLE_NOISE0)) pipe_header(A, st, sc, s, ps, rover, lane, valid, snap, dry);
     }   // phase
     __syncthreads();
     // ---- tail part 2: the A rows of a live partial

@@ -2,9 +2,10 @@
 """Turns an `ncu --set full --import-source on` report into the markdown summary committed under profiles/.
 
   python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_<what>.md
-  python tools/ncu_summary.py gpurun_out/prof.ncu-rep --counters C2_strict profiles/rNN_<what>.md
+  python tools/ncu_summary.py gpurun_out/prof.ncu-rep --counters C2_strict profiles/rNN_<what>.md K T pipe|mono
       (additionally records warp-instructions / DRAM bytes per launch of the first captured launch under that key in
-       profiles/kernel_counters.json, which bench.py reads for roofline.issue / roofline.traffic)
+       profiles/kernel_counters.json -- with the K, T and kernel variant they were captured at -- which bench.py reads
+       for roofline.issue / roofline.traffic and uses as they are ONLY for that configuration)
 
 Runs here (no GPU needed: `ncu -i` only reads the report).
 """
@@ -28,10 +29,14 @@ RAW_KEYS = [
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-    "l1tex__t_bytes.sum.per_second", "lts__t_bytes.sum.per_second", "lts__t_bytes.sum",
-    "lts__t_sectors_op_read.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
-    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sector_hit_rate.pct", "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "lts__t_sector_op_read_hit_rate.pct", "lts__t_sectors.sum", "lts__t_sectors.sum.per_second",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second", "dram__bytes.sum.per_second",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__average_warp_latency_per_inst_issued.ratio",
 ]
@@ -42,7 +47,7 @@ def ncu_csv(rep, page):
     return list(csv.reader(io.StringIO(out)))
 
 
-def update_counters(raw, key, source):
+def update_counters(raw, key, source, K=None, T=None, variant=None):
     import json
     import os
     hdr = raw[0]
@@ -53,7 +58,9 @@ def update_counters(raw, key, source):
     dram = sum(f(k) * scale.get(units.get(k, "byte"), 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "kernel_counters.json")
     allc = json.load(open(path)) if os.path.exists(path) else {}
-    allc[key] = {"warp_inst_per_launch": f("smsp__inst_executed.sum"), "dram_bytes_per_launch": dram,
+    allc[key] = {"K": K, "T": T, "variant": variant,
+                 "warp_inst_per_launch": f("smsp__inst_executed.sum"), "dram_bytes_per_launch": dram,
+                 "l2_sectors_per_launch": f("lts__t_sectors.sum"), "l2_hit_pct": f("lts__t_sector_hit_rate.pct"),
                  "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                  "l1_hit_pct": f("l1tex__t_sector_hit_rate.pct"), "kernel": d.get("Kernel Name"),
                  "source": f"{source} (ncu --set full, first captured launch)"}
@@ -65,10 +72,13 @@ def main():
     raw = ncu_csv(rep, "raw")
     hdr, units = raw[0], raw[1]
     if len(sys.argv) >= 5 and sys.argv[2] == "--counters":
-        update_counters(raw, sys.argv[3], sys.argv[4])
+        extra = sys.argv[5:8]
+        update_counters(raw, sys.argv[3], sys.argv[4], int(extra[0]) if len(extra) > 0 else None,
+                        int(extra[1]) if len(extra) > 1 else None, extra[2] if len(extra) > 2 else None)
     print(f"# ncu summary of `{rep.split('/')[-1]}`\n")
-    print("`ncu --set full --clock-control none --import-source on` (one replayed launch per row; times under the "
-          "profiler are cold-cache and serialised and are NOT bench numbers).\n")
+    print("`ncu --set full --clock-control none` (tools/prof_all.sh; one replayed launch per row; times under the "
+          "profiler are cold-cache and serialised and are NOT bench numbers; the SASS section is present when the "
+          "capture was taken with `--import-source on`).\n")
     for r in raw[2:]:
         d = dict(zip(hdr, r))
         print(f"## launch {d.get('ID')}: `{d.get('Kernel Name')}` grid {d.get('Grid Size')} block {d.get('Block Size')}\n")

@@ -761,7 +761,7 @@ __device__ __forceinline__ bool ll_ok(const uint4& l, uint32_t seq) { return l.y
 template <typename PS>
 __device__ __forceinline__ void pipe_header(const FusedArgs& A, const MppiState& st, const SampleConsts& sc,
                                             const Smem& s, PS& ps, int rover, int lane, bool valid, unsigned snapshot_key,
-                                            bool dry)
+                                            bool dry, const float* uhist)
 {
     const MppiParams& p = A.p;
     const int T = p.T, K = p.K;
@@ -824,7 +824,43 @@ __device__ __forceinline__ void pipe_header(const FusedArgs& A, const MppiState&
         const float v1 = (j == 0) ? __int_as_float(arg_w) : (j == 1) ? s2_b : __uint_as_float(nan_b);
         st_ll((push ? A.peers.ll[r] + flat_off : local_slot) + j, v0, v1, seq);
     }
-    if (lane == 0 && !dry) { s.red_i[62] = dead ? 0 : __popc(mask); trace_stamp(A, 5); }
+    int n_e = dead ? 0 : __popc(mask);
+    if (lane == 0 && !dry) trace_stamp(A, 5);
+
+    // ---- the A rows of a live partial, by this same warp when the block kept its sampled u in shared memory: plain
+    //      reads, no block barrier, and the code is covered by the warm-up trip -- the rows leave ~0.2 us after the header
+    //      instead of ~1.1 us (they are what the updater's fold waits for).  Summation order = accumulate_rows': G
+    //      groups of entries (e = g, g + G, ...) summed separately, then the group sums folded in order.
+    if (uhist != nullptr && n_e > 0) {
+        __syncwarp();
+        const int P = ll_pairs(T), B = blockDim.x;
+        const int G = (B >= 2 * P && n_e > 1) ? B / P : 1;
+        for (int pr = lane; pr < P; pr += 32) {
+            const int t = 2 * pr;
+            float a1a = 0.f, a1b = 0.f, a2a = 0.f, a2b = 0.f;
+            for (int g = 0; g < G && g < n_e; ++g) {
+                float g1a = 0.f, g1b = 0.f, g2a = 0.f, g2b = 0.f;
+                for (int e = g; e < n_e; e += G) {
+                    const float* u = uhist + (size_t)t * 64 + (s.list_i[e] & 31);      // (& 31: stale list in the dry trip)
+                    const float we = s.list_w[e];
+                    g1a += we * u[0];
+                    g2a += we * u[32];
+                    if (t + 1 < T) { g1b += we * u[64]; g2b += we * u[96]; }
+                }
+                a1a += g1a; a1b += g1b; a2a += g2a; a2b += g2b;
+            }
+            if (!dry) {
+                for (int r = 0; r < ndst; ++r) {
+                    uint4* d = (push ? A.peers.ll[r] + flat_off : local_slot) + kLLHeaderLines + pr;
+                    st_ll(d, a1a, a1b, seq);
+                    st_ll(d + P, a2a, a2b, seq);
+                }
+            }
+        }
+        if (lane == 0 && !dry) trace_stamp(A, 11);
+        n_e = 0;                                    // nothing left for pipe_rows
+    }
+    if (lane == 0 && !dry) s.red_i[62] = n_e;
 }
 
 // Worker tail, part 2 (every thread, after a barrier): the A rows of a live partial.
@@ -1723,7 +1759,7 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
 #ifndef MPPI_DRY_ROLE
 #define MPPI_DRY_ROLE ROLE_OBST            // A/B knob: which idle warp runs the warm-up trip (measured: no difference)
 #endif
-    if (role == (dry ? MPPI_DRY_ROLE : ROLE_NOISE0)) pipe_header(A, st, sc, s, ps, rover, lane, valid, snap, dry);
+    if (role == (dry ? MPPI_DRY_ROLE : ROLE_NOISE0)) pipe_header(A, st, sc, s, ps, rover, lane, valid, snap, dry, uhist);
     }   // phase
     __syncthreads();
     // ---- tail part 2: the A rows of a live partial

@@ -7,10 +7,11 @@ Two modes, both new work (the reference is single-GPU):
   number of ranks.  The only exchange is the softmax partial {M, S, argmin, S2, A1[T], A2[T]} (4 + 2T floats per
   rank, 816 B at T = 100); every rank folds the partials in rank order, so all ranks hold the identical updated
   nominal without a broadcast.  Two transports:
-    "p2p"  (default on GPUs) the exchange is fused into the step's single launch: every block stores its softmax
-           partial into every rank over NVLink (buffers mapped with CUDA IPC) as soon as it has it; the rank's last
-           block releases a flag per peer, waits for the world's flags and folds all world x nblocks partials in global
-           block order -- no collective call, no second kernel, bitwise the result of the unsharded launch;
+    "p2p"  (default on GPUs) the exchange is fused into the step's single launch: every worker block stores its softmax
+           partial as flag-in-data lines {value, sequence} into every rank over NVLink (buffers mapped with CUDA IPC) as
+           soon as it has it; every rank's updater block polls the world x nblocks slots in its own memory and folds
+           them in global block order -- no collective call, no second kernel, no fence, bitwise the result of the
+           unsharded launch over the same blocks (many-block launches: the rank folds first, rank partials are exchanged);
     "nccl" one all_gather_into_tensor + the combine kernel (also the path the CPU/gloo tests cover).
 * rover sharding (BASELINE config 4): rovers are independent controllers; rank g owns a contiguous block of
   rovers and nothing is exchanged.

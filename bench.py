@@ -660,11 +660,14 @@ def roofline_object(kernel_kind, units, T, dur_s, pk, lp, counters, share, kerne
         "hbm": {"achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"]},
         "fp32": {"achieved": fp32_ach, "peak": lp["fp32_tflops"], "unit": "TFLOP/s", "frac": fp32_ach / lp["fp32_tflops"],
                  "flop_per_sample_step": FLOP_PER_SAMPLE_STEP, "peak_source": "measured live: " + lp["how"]},
-        "l2_gather": {"achieved": sect_ach, "peak": lp["l2_gather_gsectors"], "unit": "Gsector/s",
-                      "frac": sect_ach / lp["l2_gather_gsectors"],
+        "l2_gather": {"algorithmic": sect_ach, "peak": lp["l2_gather_gsectors"], "unit": "Gsector/s",
+                      "ratio_if_nothing_were_staged": sect_ach / lp["l2_gather_gsectors"],
                       "sectors_per_sample_step": GATHER_SECTORS_PER_SAMPLE_STEP,
                       "peak_source": "measured live (random 32-byte-sector gathers from L2)",
-                      "note": "upper bound of what the lookups would cost if none were staged in shared memory / L1"},
+                      "note": "NOT an achieved fraction: the worst-case sector count of the lookups (5 per sample-step) "
+                              "over the launch time, against the L2 random-gather rate -- what the L2 would have to "
+                              "deliver if shared memory / L1 staged nothing; above 1 means the path only works BECAUSE "
+                              "they do (measured L2 traffic: l2_measured)"},
     }
     if counters.get("dram_bytes_per_launch"):
         t = counters["dram_bytes_per_launch"] / dur_s / 1e9

@@ -288,25 +288,63 @@ def test_synthetic_crater_dem_is_the_reference_surface_if_present():
     assert np.ptp(ours) > 4.0                                   # a real crater field (rims ~3.9 m, floors ~-1 m), not a plane
 
 
-def test_committed_bench_line_carries_the_measurement_contract():
-    """The last C2 line measured on a B200 this round (profiles/r1_bench/) has every key the measurement contract
-    names, with consistent values -- a schema check of what bench.py's GPU arm emits (that arm cannot run here)."""
+def _fracs(obj, path=""):
+    if isinstance(obj, dict):
+        for k, v in obj.items():
+            if k == "frac" and isinstance(v, (int, float)):
+                yield path, v
+            else:
+                yield from _fracs(v, f"{path}/{k}")
+
+
+def test_committed_bench_lines_carry_the_measurement_contract():
+    """The lines measured on B200s this round (profiles/r2_bench/) have every key the measurement contract names, with
+    consistent values -- a schema check of what bench.py's GPU arm emits (that arm cannot run here).  No roofline
+    fraction may exceed 1 (round 1 printed issue.frac = 2.78 from counters of another configuration), the bound is named
+    after what binds, and the same-run sub-objects carry passed equality checks."""
     import glob
     import json
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    path = sorted(glob.glob(os.path.join(root, "profiles", "r1_bench", "r1o_bench_c2_strict.json")))[-1]
-    d = json.loads([l for l in open(path) if l.startswith("{")][0])
-    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
-        assert k in d, k
-    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32"
-    assert "C2" in d["config"]["workload"] and "model" not in d["config"] and d["warmup"] >= 3
-    assert d["gpu_launches"] == d["steps"]                                   # ONE fused launch per control iteration
+    lines = {}
+    for path in sorted(glob.glob(os.path.join(root, "profiles", "r2_bench", "*.json"))):
+        lines[os.path.basename(path)] = json.loads([l for l in open(path) if l.startswith("{")][0])
+    assert "c2_strict_default.json" in lines and len(lines) >= 10
+    for name, d in lines.items():
+        if d.get("impl") == "reference":
+            assert d["gpu_launches"] == 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+            continue
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+            assert k in d, (name, k)
+        assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32" and d["warmup"] >= 3
+        assert "model" not in d["config"] and "workload" in d["config"]
+        r = d["roofline"]
+        assert r["bound"] in ("latency", "issue") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        for where, f in _fracs(r):
+            assert 0.0 <= f <= 1.0, (name, where, f)
+        if "issue" in r:
+            assert r["issue"]["extrapolated"] in (False, True)
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert d["e2e"]["value"] < d["value"] * 1.001
+    d = lines["c2_strict_default.json"]
+    assert d["n_gpus"] == 1 and "C2" in d["config"]["workload"] and d["gpu_launches"] == d["steps"]
     assert abs(d["value"] - 4096 * 100 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
-    r = d["roofline"]
-    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
-    assert d["e2e"]["h2d_bytes_per_step"] == 48 and d["e2e"]["d2h_bytes_per_step"] == 8 and d["e2e"]["value"] < d["value"]
-    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
-    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    assert d["ms_per_step"] * 1e3 < 100.0                                    # BASELINE target: C2 under 100 us
+    assert d["roofline"]["bound"] == "latency" and d["roofline"]["traffic"] > 0 and d["roofline"]["issue"]["extrapolated"] is False
+    assert 0.5 < d["roofline"]["kernel_share_of_step"] <= 1.0                    # measured, not asserted
+    assert d["e2e"]["h2d_bytes_per_step"] == 48 and d["e2e"]["d2h_bytes_per_step"] == 8
+    assert d["latency_us"]["steps"] >= 1000                                     # p50 / p99 do not depend on --steps
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["reference_script"]["kind"] == "reference"
+    assert cb["reference_script"]["cores"] == 1 and cb["reference_script"]["value"] < cb["value"]
+    assert d["ms_per_step"] * 1e3 < 100.0                                       # BASELINE target: C2 under 100 us
+    sc = d["sharded_check"]
+    assert sc["passed"] and sc["p2p_bitwise"] and sc["argmin_equal"] and sc["lambdas"] == [0.3, 2000.0]
+    assert d["c3"]["weak"]["check"]["passed"] and d["c3"]["weak"]["K_per_gpu"] == 262144
+    assert d["c4"]["check"]["passed"] and d["c4"]["rovers_per_gpu"] == 512
+    # the multi-GPU lines: same per-GPU workload, more GPUs
+    for n in (2, 4, 8):
+        m = lines[f"c2_strict_n{n}.json"]
+        assert m["n_gpus"] == n and m["config"]["K_total"] == n * 4096 and m["scaling"] == "weak"
+        assert m["value"] > lines["c2_strict_n1.json"]["value"]
+    assert lines["c5many_strict_ext.json"]["roofline"]["hbm_measured"]["frac"] > 0.05   # the many-start C5 leaves L2

@@ -767,7 +767,7 @@ def main():
     warm_ms = ctx.timed_loop(one_step, min(max(args.steps, 100), 1000), 200000, False)
 
     # ---- share of the step spent in the fused kernel: the library's own events around the launch vs ours
-    share = None
+    share = lib_lat = None
     if n_gpus == 1:
         capi.check(core.L.mppi_enable_timing(core.h, 1), "mppi_enable_timing")
         ours, theirs = [], []
@@ -783,6 +783,7 @@ def main():
             torch.cuda.synchronize(dev)
             ours.append(e0.elapsed_time(e1) * 1e3)
             theirs.append(us.value)
+        lib_lat = core.latency_stats() if hasattr(core.L, "mppi_latency_stats") else None
         capi.check(core.L.mppi_enable_timing(core.h, 0), "mppi_enable_timing")
         share = float(np.sum(theirs) / np.sum(ours))
 
@@ -901,7 +902,9 @@ def main():
                            "mean": float(lat_ms.mean() * 1e3), "max": float(lat_ms.max() * 1e3), "steps": int(len(lat_ms)),
                            "steps_over_2x_p50": int((lat_ms > 2 * np.median(lat_ms)).sum()),
                            "timed_region_p50": float(np.median(per_step_ms) * 1e3),
-                           "note": "device time of back-to-back launches on this rank (CUDA events), L2 flushed between them"},
+                           "library_ring": lib_lat,
+                           "note": "device time of back-to-back launches on this rank (CUDA events), L2 flushed between them; "
+                                   "library_ring = mppi_latency_stats over the 50 launches of the share leg"},
             "warm_l2": {"ms_per_step": float(warm_ms.mean()), "p50_us": float(np.median(warm_ms) * 1e3),
                         "value": K_total * T / float(warm_ms.mean() * 1e-3)},
             "e2e": e2e,

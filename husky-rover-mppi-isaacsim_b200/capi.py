@@ -111,6 +111,8 @@ SYMBOLS = {
     "mppi_get_outputs": (C.c_int, [_H, C.POINTER(MppiOutputs)]),
     "mppi_enable_timing": (C.c_int, [_H, C.c_int32]),
     "mppi_last_step_us": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "mppi_latency_stats": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                     C.POINTER(C.c_int32)]),
     "mppi_set_trace": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
     "mppi_measure_peaks": (C.c_int, [C.c_int32, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float)]),

@@ -168,6 +168,15 @@ class Core:
     def sim_rollout(self, state, stream=None):
         capi.check(self.L.mppi_sim_rollout(self.h, C.byref(state), self._stream(stream)), "mppi_sim_rollout")
 
+    def enable_timing(self, on: bool = True):
+        capi.check(self.L.mppi_enable_timing(self.h, 1 if on else 0), "mppi_enable_timing")
+
+    def latency_stats(self) -> dict:
+        """p50 / p99 / max device time (us) of the last up-to-1024 completed steps since enable_timing()."""
+        a, b, c, n = C.c_float(), C.c_float(), C.c_float(), C.c_int32()
+        capi.check(self.L.mppi_latency_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)), "mppi_latency_stats")
+        return dict(p50_us=float(a.value), p99_us=float(b.value), max_us=float(c.value), n=int(n.value))
+
     def partial_floats(self) -> int:
         return int(self.L.mppi_partial_floats(self.T))
 

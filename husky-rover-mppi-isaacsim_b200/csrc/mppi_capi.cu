@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
+#include <vector>
 
 using namespace mppi;
 
@@ -41,6 +43,9 @@ struct MppiHandle {
     cudaEvent_t ev0, ev1;
     bool timing;
     bool timed_valid;
+    // latency ring (mppi_latency_stats): the event pairs of the last kLatRing timed steps
+    cudaEvent_t* lat_ev;         // [2 * kLatRing], created on the first timed step
+    uint32_t lat_count;          // timed steps so far
     unsigned long long* trace;   // optional device buffer for kernel timeline stamps (mppi_set_trace)
     // sample-sharded multi-GPU exchange over peer memory (mppi_comm_*)
     void* comm_local;            // this rank's exchange allocation: [LL lines (flat variant)] + [2][world][stride] floats + [2][world] flags
@@ -61,6 +66,7 @@ struct MppiHandle {
     const float* desc_dem; int desc_gs, desc_w, desc_h; bool desc_ok;
 };
 
+static constexpr int kLatRing = 1024;
 static thread_local char g_cuda_err[256];
 
 static int cuda_fail(cudaError_t e, const char* where)
@@ -204,6 +210,7 @@ extern "C" int mppi_destroy(MppiHandle* h)
     if (h->cmd_pinned) cudaFreeHost(h->cmd_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->lat_ev) { for (int i = 0; i < 2 * kLatRing; ++i) if (h->lat_ev[i]) cudaEventDestroy(h->lat_ev[i]); delete[] h->lat_ev; }
     delete h;
     return MPPI_OK;
 }
@@ -376,7 +383,18 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
             else a.tile.w = a.tile.h = 0;
         }
     }
-    if (h->timing) CK(cudaEventRecord(h->ev0, s));
+    cudaEvent_t ring0 = nullptr, ring1 = nullptr;
+    if (h->timing) {
+        if (!h->lat_ev) {
+            h->lat_ev = new (std::nothrow) cudaEvent_t[2 * kLatRing]();
+            if (!h->lat_ev) return MPPI_ERR_ALLOC;
+            for (int i = 0; i < 2 * kLatRing; ++i) CK(cudaEventCreate(&h->lat_ev[i]));
+        }
+        ring0 = h->lat_ev[2 * (h->lat_count % kLatRing)];
+        ring1 = h->lat_ev[2 * (h->lat_count % kLatRing) + 1];
+        CK(cudaEventRecord(h->ev0, s));
+        CK(cudaEventRecord(ring0, s));
+    }
     // NVTX range around the launch (a no-op without a profiler attached): mppi_step [pipe | mono]
     nvtxRangePushA(h->pipe ? "mppi_step [pipelined kernel]" : "mppi_step [monolithic kernel]");
     cudaError_t e;
@@ -386,7 +404,7 @@ static int do_step(MppiHandle* h, const MppiState* state, const MppiState* state
         e = MPPI_BY_NS(h->p, launch_fused(a, proj, n_rovers, h->block, s));
     nvtxRangePop();
     if (e != cudaSuccess) return cuda_fail(e, "launch_fused");
-    if (h->timing) { CK(cudaEventRecord(h->ev1, s)); h->timed_valid = true; }
+    if (h->timing) { CK(cudaEventRecord(ring1, s)); CK(cudaEventRecord(h->ev1, s)); h->timed_valid = true; ++h->lat_count; }
     return MPPI_OK;
 }
 
@@ -675,6 +693,7 @@ extern "C" int mppi_enable_timing(MppiHandle* h, int32_t on)
     if (!h) return MPPI_ERR_INVALID_ARG;
     h->timing = on != 0;
     h->timed_valid = false;
+    h->lat_count = 0;
     return MPPI_OK;
 }
 
@@ -685,6 +704,27 @@ extern "C" int mppi_last_step_us(MppiHandle* h, float* us)
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     *us = ms * 1000.f;
+    return MPPI_OK;
+}
+
+extern "C" int mppi_latency_stats(MppiHandle* h, float* p50_us, float* p99_us, float* max_us, int32_t* n_out)
+{
+    if (!h || !p50_us || !p99_us || !max_us || !n_out) return MPPI_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    std::vector<float> us;
+    const uint32_t have = std::min<uint32_t>(h->lat_count, (uint32_t)kLatRing);
+    for (uint32_t i = 0; i < have && h->lat_ev; ++i) {
+        if (cudaEventQuery(h->lat_ev[2 * i + 1]) != cudaSuccess) continue;      // still in flight: not counted
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->lat_ev[2 * i], h->lat_ev[2 * i + 1]) == cudaSuccess) us.push_back(ms * 1000.f);
+    }
+    cudaGetLastError();
+    *n_out = (int32_t)us.size();
+    if (us.empty()) { *p50_us = *p99_us = *max_us = 0.f; return MPPI_OK; }
+    std::sort(us.begin(), us.end());
+    *p50_us = us[us.size() / 2];
+    *p99_us = us[std::min(us.size() - 1, (size_t)(0.99 * (double)us.size()))];
+    *max_us = us.back();
     return MPPI_OK;
 }
 
@@ -700,7 +740,8 @@ extern "C" int mppi_set_trace(MppiHandle* h, uint64_t* trace_dev, int32_t* nbloc
 namespace mppi { namespace costmap {
 cudaError_t build(const double* obstacles_dev, int n_obs, double x0, double y0, int cms, double hw, double r_robot,
                   double radius_scale, double inflate, double power, uint8_t* mask, float* tmp, float* dist, float* minmax,
-                  float* costmap, cudaStream_t s);
+                  float* costmap, float* dist_out, uint8_t* mask_out, cudaStream_t s);
+size_t workspace_cells(int cms);      // the builder keeps mask / distances in a wavefront-major layout (costmap_kernels.cu)
 } }
 
 struct CostmapWorkspace {          // grown on demand, one per process (the builder is not re-entrant)
@@ -720,7 +761,7 @@ extern "C" int mppi_build_costmap(int32_t device, const double* obstacles_host, 
         return (costmap_size > 1024) ? MPPI_ERR_UNSUPPORTED : MPPI_ERR_INVALID_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     CK(cudaSetDevice(device));
-    const size_t cells = (size_t)costmap_size * costmap_size;
+    const size_t cells = mppi::costmap::workspace_cells(costmap_size);
     if (g_cm.device != device || g_cm.cells < cells) {
         if (g_cm.mask) { cudaFree(g_cm.mask); cudaFree(g_cm.tmp); cudaFree(g_cm.dist); cudaFree(g_cm.minmax); }
         g_cm.mask = nullptr; g_cm.cells = 0;
@@ -742,10 +783,8 @@ extern "C" int mppi_build_costmap(int32_t device, const double* obstacles_host, 
         CK(cudaMemcpyAsync(g_cm.obstacles, obstacles_host, (size_t)n_obs * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
     cudaError_t e = mppi::costmap::build(g_cm.obstacles, n_obs, origin_x, origin_y, costmap_size, half_width, r_robot,
                                          radius_scale, inflate, power, g_cm.mask, g_cm.tmp, g_cm.dist, g_cm.minmax,
-                                         costmap_dev, s);
+                                         costmap_dev, distance_dev, mask_dev, s);
     if (e != cudaSuccess) return cuda_fail(e, "mppi_build_costmap");
-    if (distance_dev) CK(cudaMemcpyAsync(distance_dev, g_cm.dist, cells * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    if (mask_dev) CK(cudaMemcpyAsync(mask_dev, g_cm.mask, cells, cudaMemcpyDeviceToDevice, s));
     return MPPI_OK;
 }
 

@@ -278,6 +278,10 @@ int mppi_get_outputs(MppiHandle *h, MppiOutputs *out);
  * profiling aid, enabled with mppi_enable_timing(h, 1). Synchronises the stream. */
 int mppi_enable_timing(MppiHandle *h, int32_t on);
 int mppi_last_step_us(MppiHandle *h, float *us);
+/* p50 / p99 / max device time (microseconds) over the last up-to-1024 steps issued since mppi_enable_timing(h, 1) that
+ * have completed (n_out of them): the control-update latency record SURVEY.md 8d asks for, kept inside the library so
+ * that a deployed loop can read it without a profiler.  Does not synchronise (steps still in flight are left out). */
+int mppi_latency_stats(MppiHandle *h, float *p50_us, float *p99_us, float *max_us, int32_t *n_out);
 
 /* Profiling aid: when trace_dev != NULL every block of rover 0 stores 32 64-bit words per step: slots 0-6 and 8-15
  * are %globaltimer nanoseconds of the kernel's phases (entry, set-up done, rollout start / end, roles joined, partial

@@ -277,6 +277,21 @@ def test_two_handles_on_two_devices_in_one_process():
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1]["argmin"] == res[1][1]["argmin"]
 
 
+def test_library_latency_ring():
+    """mppi_latency_stats: p50 / p99 / max over the steps timed since mppi_enable_timing, without a profiler."""
+    import torch
+    core, *_ = make_core(1024, 50)
+    st = state_struct(default_state())
+    core.enable_timing(True)
+    for i in range(12):
+        core.step(st, seed=1, offset=i)
+    torch.cuda.synchronize()
+    s = core.latency_stats()
+    assert s["n"] == 12 and 5.0 < s["p50_us"] <= s["p99_us"] <= s["max_us"] < 5000.0
+    core.enable_timing(False)
+    core.close()
+
+
 def test_fused_peer_exchange_world1_equals_plain_step(oracle):
     """The sample-sharded step with the exchange fused into the launch (mppi_step_sharded), world = 1: the rank
     partial goes through the exchange buffer and the flag hand-shake and must reproduce mppi_step."""

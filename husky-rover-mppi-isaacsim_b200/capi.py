@@ -116,6 +116,7 @@ SYMBOLS = {
     "mppi_set_trace": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int32)]),
     "mppi_measure_peaks": (C.c_int, [C.c_int32, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float)]),
+    "mppi_test_timestamp": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_test_detmath": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mppi_test_noise": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),

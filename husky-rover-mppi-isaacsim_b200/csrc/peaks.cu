@@ -58,6 +58,22 @@ float time_ms(cudaEvent_t e0, cudaEvent_t e1)
 
 }  // namespace
 
+// One thread stores %globaltimer: a timestamp in the SAME clock as the kernel-internal stamps of mppi_set_trace, for
+// splitting the time between a launch's neighbours in the stream and its first / last instruction (tools/launch_gap.py).
+__global__ void timestamp_kernel(unsigned long long* out)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *out = t;
+}
+
+extern "C" int mppi_test_timestamp(uint64_t* out_dev, void* stream)
+{
+    if (!out_dev) return MPPI_ERR_INVALID_ARG;
+    timestamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(out_dev));
+    return cudaGetLastError() == cudaSuccess ? MPPI_OK : MPPI_ERR_CUDA;
+}
+
 extern "C" int mppi_measure_peaks(int32_t device, uint64_t l2_window_bytes, float* fp32_tflops, float* l2_gather_gsectors,
                                   float* l2_gather_gbs)
 {

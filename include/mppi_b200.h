@@ -298,6 +298,9 @@ int mppi_set_trace(MppiHandle *h, uint64_t *trace_dev, int32_t *nblocks_out);
 int mppi_measure_peaks(int32_t device, uint64_t l2_window_bytes, float *fp32_tflops, float *l2_gather_gsectors,
                        float *l2_gather_gbs);
 
+/* Measurement aid: a one-thread kernel that stores %globaltimer (the clock of the mppi_set_trace stamps) into *out_dev. */
+int mppi_test_timestamp(uint64_t *out_dev, void *stream);
+
 /* Test hook: evaluates the specified ("det") math on the device. fn: 0 sincos, 1 sincos(2*pi*u), 2 log, 3 exp, 4 atan.
  * x, y0, y1 are device pointers [n]. */
 int mppi_test_detmath(int32_t fn, const float *x_dev, float *y0_dev, float *y1_dev, int32_t n, void *stream);

@@ -530,7 +530,6 @@ extern "C" int mppi_comm_connect(MppiHandle* h, int32_t rank, int32_t world, con
     h->peers.world = world;
     h->peers.nblocks = h->comm_nblocks;
     h->peers.seq = 0;
-    h->peers.pull = getenv("MPPI_EXCHANGE_PULL") ? atoi(getenv("MPPI_EXCHANGE_PULL")) : 0;
     return MPPI_OK;
 }
 

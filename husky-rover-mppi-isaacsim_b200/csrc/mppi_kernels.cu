@@ -725,29 +725,19 @@ __device__ __forceinline__ void block_update(const FusedArgs& A, const MppiState
 // 16-byte line {v0, seq, v1, seq}; volatile accesses go straight to L2 (or over NVLink into the peer's L2).
 __device__ __forceinline__ void st_ll(uint4* line, float v0, float v1, uint32_t seq)
 {
-#ifdef MPPI_AB_LL_GPU_SCOPE
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};"
-#else
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
-#endif
                  ::"l"(line), "r"(__float_as_uint(v0)), "r"(seq), "r"(__float_as_uint(v1)), "r"(seq) : "memory");
 }
 __device__ __forceinline__ uint4 ld_ll(const uint4* line)
 {
     uint4 v;
-#ifdef MPPI_AB_LL_GPU_SCOPE
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-#else
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-#endif
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(line) : "memory");
     return v;
 }
-#ifdef MPPI_AB_NOSLEEP
-#define MPPI_POLL_SLEEP() do { } while (0)
-#else
+// (relaxed.gpu instead of volatile accesses, and polling without the 20 ns back-off, were measured at N = 1: no
+// difference -- profiles/r2_ab_recurrence_and_poll_scope.txt)
 #define MPPI_POLL_SLEEP() __nanosleep(20)
-#endif
 __device__ __forceinline__ bool ll_ok(const uint4& l, uint32_t seq) { return l.y == seq && l.w == seq; }
 
 // Worker tail, part 1 (ONE warp): total cost of the warp's 32 samples from the critic sums the roles left in shared
@@ -768,12 +758,11 @@ __device__ __forceinline__ void pipe_header(const FusedArgs& A, const MppiState&
     const uint32_t seq = A.ll_seq;
     const unsigned FULL = 0xffffffffu;
     const bool flat = peers_flat(A) && (rover == 0);
-    const int ndst = (flat && !A.peers.pull) ? A.peers.world : 1;
+    const int ndst = flat ? A.peers.world : 1;
     const int L = ll_lines(T);
     const size_t flat_off = flat ? (((size_t)(seq & 1u) * A.peers.world + A.peers.rank) * A.nblocks + blockIdx.x) * L : 0;
     uint4* local_slot = flat ? A.peers.ll[A.peers.rank] + flat_off
                              : A.ll + ((size_t)rover * A.nblocks + blockIdx.x) * L;
-    const bool push = flat && !A.peers.pull;
 
     // ---- cost (critics_warp.py:325-329)
     SampleAcc a;
@@ -822,7 +811,7 @@ __device__ __forceinline__ void pipe_header(const FusedArgs& A, const MppiState&
         // bit 31 of the argmin word: "this block has out-of-range / NaN counts in line 2" (sample ids are < 2^31)
         const int arg_w = arg_b | (((oob_b | nan_b) != 0u) ? (int)0x80000000 : 0);
         const float v1 = (j == 0) ? __int_as_float(arg_w) : (j == 1) ? s2_b : __uint_as_float(nan_b);
-        st_ll((push ? A.peers.ll[r] + flat_off : local_slot) + j, v0, v1, seq);
+        st_ll((flat ? A.peers.ll[r] + flat_off : local_slot) + j, v0, v1, seq);
     }
     int n_e = dead ? 0 : __popc(mask);
     if (lane == 0 && !dry) trace_stamp(A, 5);
@@ -851,7 +840,7 @@ __device__ __forceinline__ void pipe_header(const FusedArgs& A, const MppiState&
             }
             if (!dry) {
                 for (int r = 0; r < ndst; ++r) {
-                    uint4* d = (push ? A.peers.ll[r] + flat_off : local_slot) + kLLHeaderLines + pr;
+                    uint4* d = (flat ? A.peers.ll[r] + flat_off : local_slot) + kLLHeaderLines + pr;
                     st_ll(d, a1a, a1b, seq);
                     st_ll(d + P, a2a, a2b, seq);
                 }
@@ -871,8 +860,7 @@ __device__ __forceinline__ void pipe_rows(const FusedArgs& A, const MppiState& s
     const int T = A.p.T, tid = threadIdx.x;
     const uint32_t seq = A.ll_seq;
     const bool flat = peers_flat(A) && (rover == 0);
-    const bool push = flat && !A.peers.pull;
-    const int ndst = push ? A.peers.world : 1;
+    const int ndst = flat ? A.peers.world : 1;
     const int L = ll_lines(T), P = ll_pairs(T);
     const size_t flat_off = flat ? (((size_t)(seq & 1u) * A.peers.world + A.peers.rank) * A.nblocks + blockIdx.x) * L : 0;
     uint4* local_slot = flat ? A.peers.ll[A.peers.rank] + flat_off
@@ -882,7 +870,7 @@ __device__ __forceinline__ void pipe_rows(const FusedArgs& A, const MppiState& s
     if (n_e == 0) return;               // dead, or no finite cost at all (sum w = 0: the updater skips the slot)
     accumulate_rows<INJECT>(A, st, nk, s, rover, 32, n_e, [&](int pr, float a1a, float a1b, float a2a, float a2b) {
         for (int r = 0; r < ndst; ++r) {
-            uint4* d = (push ? A.peers.ll[r] + flat_off : local_slot) + kLLHeaderLines + pr;
+            uint4* d = (flat ? A.peers.ll[r] + flat_off : local_slot) + kLLHeaderLines + pr;
             st_ll(d, a1a, a1b, seq);
             st_ll(d + P, a2a, a2b, seq);
         }
@@ -900,12 +888,9 @@ __device__ __forceinline__ void pipe_rows(const FusedArgs& A, const MppiState& s
 // `dry`: warm-up pass, run once while the workers roll out -- the same code on the previous launch's lines with every
 // wait and every global store predicated off, so that instructions and kernel parameters are cached when the real
 // pass starts (see pipe_header).
-#ifdef MPPI_AB_UPD_NOINLINE
-__device__ __noinline__                  // A/B knob (measured: the generic-address parameter loads cost the updater ~2.5 us)
-#else
-__device__ __forceinline__
-#endif
-void pipe_updater(const FusedArgs& A, const MppiState& st, const Smem& s, float* hdr,
+// (As a __noinline__ function the updater would leave the workers' code where it is, but its parameter loads turn into
+// generic-address loads: +2.5 us measured, profiles/r2_ab_unroll_and_noinline.txt.)
+__device__ __forceinline__ void pipe_updater(const FusedArgs& A, const MppiState& st, const Smem& s, float* hdr,
                                              int rover, float* nominal1, float* nominal2, bool dry)
 {
     const MppiParams& p = A.p;
@@ -914,13 +899,9 @@ void pipe_updater(const FusedArgs& A, const MppiState& st, const Smem& s, float*
     const bool flat = peers_flat(A) && (rover == 0);
     const int n = A.nblocks * (flat ? A.peers.world : 1);
     const int L = ll_lines(T), P = ll_pairs(T);
-    const bool pull = flat && A.peers.pull;
     const size_t half_off = flat ? (size_t)(seq & 1u) * n * L : 0;
     const uint4* slots = flat ? A.peers.ll[A.peers.rank] + half_off : A.ll + (size_t)rover * A.nblocks * L;
-    // pull mode: the lines of rank r's blocks live in rank r's buffer (same layout everywhere) and are read over NVLink
-    auto slot_of = [&](int b) -> const uint4* {
-        return (pull ? A.peers.ll[b / A.nblocks] + half_off : slots) + (size_t)b * L;
-    };
+    auto slot_of = [&](int b) -> const uint4* { return slots + (size_t)b * L; };
     unsigned long long* tr = (A.trace != nullptr && rover == 0 && !dry) ? A.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
     float* hm = hdr;
     float* hs = hdr + n;
@@ -1135,36 +1116,30 @@ void pipe_updater(const FusedArgs& A, const MppiState& st, const Smem& s, float*
         for (int t = tid; t < T; t += B) if (!dry) { opt_v[t] = s.acc[t]; opt_w[t] = s.acc[T + t]; }
     } else {
         // the two T-step recurrences l <- l a + drive_l[t], r <- r a + drive_r[t] run on one thread each (warps 1 and 2:
-        // warp 0 is busy with the command), in register batches; same operations in the same order as a one-thread loop
+        // warp 0 is busy with the command), 16 steps per trip in registers; same operations in the same order as a
+        // one-thread loop (same-node A/B against 8-step scalar batches: 1900 vs 2900 cycles, -0.6 us per launch)
         //  -- results go to s.acc (the nominal copy is no longer needed): thread 0 is still reading the drives
         if (lane == 0 && (warp == 1 || warp == 2)) {
             const float* d = (warp == 1) ? s.nom1 : s.nom2;
             float* out = (warp == 1) ? s.acc : s.acc + T;
             float x = (warp == 1) ? st.wheel_l : st.wheel_r;
-            // batches of 8 steps: the next batch is loaded before the current one runs its 16 dependent operations
-            constexpr int N = 8;
-            const int nb = T / N;
-            float cur[N], nxt[N];
-            if (nb > 0) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) cur[i] = d[i];
-            }
-            for (int b = 0; b < nb; ++b) {
-                const bool more = b + 1 < nb;
-                if (more) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) nxt[i] = d[N * (b + 1) + i];
-                }
-#pragma unroll
-                for (int i = 0; i < N; ++i) { x = x * p.opt_a + cur[i]; cur[i] = x; }
-#pragma unroll
-                for (int i = 0; i < N; ++i) out[N * b + i] = cur[i];
-                if (more) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) cur[i] = nxt[i];
+            // batches of 16 steps held in registers: 4 vector loads, 32 dependent operations, 4 vector stores (the drive
+            // and result arrays are 16-byte aligned when T is a multiple of 4; otherwise the scalar loop below)
+            int t = 0;
+            if ((T & 3) == 0) {
+                const float a = p.opt_a;
+                for (; t + 16 <= T; t += 16) {
+                    float4 c0 = *reinterpret_cast<const float4*>(d + t), c1 = *reinterpret_cast<const float4*>(d + t + 4);
+                    float4 c2 = *reinterpret_cast<const float4*>(d + t + 8), c3 = *reinterpret_cast<const float4*>(d + t + 12);
+                    x = x * a + c0.x; c0.x = x; x = x * a + c0.y; c0.y = x; x = x * a + c0.z; c0.z = x; x = x * a + c0.w; c0.w = x;
+                    x = x * a + c1.x; c1.x = x; x = x * a + c1.y; c1.y = x; x = x * a + c1.z; c1.z = x; x = x * a + c1.w; c1.w = x;
+                    x = x * a + c2.x; c2.x = x; x = x * a + c2.y; c2.y = x; x = x * a + c2.z; c2.z = x; x = x * a + c2.w; c2.w = x;
+                    x = x * a + c3.x; c3.x = x; x = x * a + c3.y; c3.y = x; x = x * a + c3.z; c3.z = x; x = x * a + c3.w; c3.w = x;
+                    *reinterpret_cast<float4*>(out + t) = c0; *reinterpret_cast<float4*>(out + t + 4) = c1;
+                    *reinterpret_cast<float4*>(out + t + 8) = c2; *reinterpret_cast<float4*>(out + t + 12) = c3;
                 }
             }
-            for (int t = N * nb; t < T; ++t) { x = x * p.opt_a + d[t]; out[t] = x; }
+            for (; t < T; ++t) { x = x * p.opt_a + d[t]; out[t] = x; }
             if (tr != nullptr && warp == 1) tr[26] = (unsigned long long)clock64();
         }
         __syncthreads();
@@ -1514,11 +1489,6 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     float* nominal2 = A.nominal2 + (size_t)rover * T;
     // (the updater block's code is placed AFTER the workers' -- see the end of the kernel)
     if (__builtin_expect(!is_updater, 1)) {
-#ifdef MPPI_AB_PAD
-    // A/B knob: shifts every following instruction of the workers' code by 16 x MPPI_AB_PAD bytes (layout probe)
-#pragma unroll
-    for (int pad_i = 0; pad_i < MPPI_AB_PAD; ++pad_i) asm volatile("nanosleep.u32 0;");
-#endif
     if (tid == 0) {
         for (int i = 0; i < kPipeStages; ++i) {
             mbar_init(&ps.full_u[i], 32); mbar_init(&ps.empty_u[i], 32);
@@ -1756,10 +1726,9 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     }   // !dry: roles
 
     // ---- tail part 1: cost, block partial, header lines (one warp; see pipe_header for the dry trip)
-#ifndef MPPI_DRY_ROLE
-#define MPPI_DRY_ROLE ROLE_OBST            // A/B knob: which idle warp runs the warm-up trip (measured: no difference)
-#endif
-    if (role == (dry ? MPPI_DRY_ROLE : ROLE_NOISE0)) pipe_header(A, st, sc, s, ps, rover, lane, valid, snap, dry, uhist);
+    // (which idle warp runs the warm-up trip -- obstacle, wheels, filter, chain -- makes no difference at the end of the
+    // launch: profiles/r2_ab_dry_role.txt)
+    if (role == (dry ? ROLE_OBST : ROLE_NOISE0)) pipe_header(A, st, sc, s, ps, rover, lane, valid, snap, dry, uhist);
     }   // phase
     __syncthreads();
     // ---- tail part 2: the A rows of a live partial
@@ -1778,9 +1747,6 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
 #endif
             for (int t = tid; t < T; t += kPipeThreads) { s.nom1[t] = nominal1[t]; s.nom2[t] = nominal2[t]; }
             __syncthreads();
-#ifdef MPPI_AB_UPD_LATE
-            if (pass == 1) { const unsigned long long t_in = globaltimer_ns(); while (globaltimer_ns() - t_in < 18000ull) __nanosleep(1000); }
-#endif
             // the updater's kept list and header values overlay the rings / tile region it does not use
             Smem su = s;
             float* ubase = smem_raw + pipe_smem_offset_floats(T);

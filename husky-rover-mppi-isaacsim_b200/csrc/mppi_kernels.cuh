@@ -49,9 +49,6 @@ struct PeerComm {
     int32_t rank, world;              // world == 0: no peer exchange
     int32_t nblocks;                  // blocks per rank the buffers were laid out for
     uint32_t seq;                     // step sequence number (parity = seq & 1 selects the buffer half)
-    int32_t pull;                     // flat variant: 0 = every worker block PUSHES its lines into every rank's buffer;
-                                      // 1 = it stores them into its own rank's buffer only and the updaters PULL (poll
-                                      // the other ranks' buffers over NVLink): no peer writes at all
 };
 
 // Device-resident closed loop (mppi_run_closed_loop): the plant of MPPI_Controller.run (MPPI_isaac.py:755-805) is the

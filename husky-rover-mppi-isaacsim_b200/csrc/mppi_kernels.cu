@@ -20,6 +20,7 @@
 
 #include <math_constants.h>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -1463,6 +1464,25 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
         }
     }
 
+    // Programmatic dependent launch (back-to-back steps: closed loop, un-flushed streams).  Every block lets the NEXT
+    // launch in the stream be scheduled at once: its blocks take the SMs this launch's workers leave, initialise their
+    // barriers, and then stop at griddepcontrol.wait -- which returns when THIS grid has completed and its writes
+    // (nominal, loop state, running minimum) are visible.  Nothing above the wait reads or writes global memory that
+    // a launch produces; with an ordinary launch on either side both instructions do nothing.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!is_updater && tid == 0) {
+        for (int i = 0; i < kPipeStages; ++i) {
+            mbar_init(&ps.full_u[i], 32); mbar_init(&ps.empty_u[i], 32);
+            mbar_init(&ps.empty_a[i], 32);
+            mbar_init(&ps.full_b[i], 32);
+        }
+        ps.a_ready = 0; ps.b_done[0] = 0; ps.b_done[1] = 0;
+        mbar_init(&ps.tile_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     if (A.loop.state != nullptr && *reinterpret_cast<volatile const int32_t*>(A.loop.ctl + 1) != 0) return;   // goal reached
     const MppiState st = (A.loop.state != nullptr) ? *A.loop.state : ((A.states != nullptr) ? A.states[rover] : A.state);
     const MppiTerrain tr = (A.terrains != nullptr) ? A.terrains[rover] : A.terrain;
@@ -1490,15 +1510,6 @@ mppi_fused_pipe_kernel(const __grid_constant__ FusedArgs A)
     // (the updater block's code is placed AFTER the workers' -- see the end of the kernel)
     if (__builtin_expect(!is_updater, 1)) {
     if (tid == 0) {
-        for (int i = 0; i < kPipeStages; ++i) {
-            mbar_init(&ps.full_u[i], 32); mbar_init(&ps.empty_u[i], 32);
-            mbar_init(&ps.empty_a[i], 32);
-            mbar_init(&ps.full_b[i], 32);
-        }
-        ps.a_ready = 0; ps.b_done[0] = 0; ps.b_done[1] = 0;
-        mbar_init(&ps.tile_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // The TMA copy of the DEM tile starts before the block even synchronises, so that the tile lands while the
         // nominal is loaded and the noise / filter stages fill the pipeline.
         if (tg.w > 0) {
@@ -2020,12 +2031,25 @@ cudaError_t launch_fused_pipe(const FusedArgs& a, int proj, int n_rovers, cudaSt
     const size_t upd = (pipe_smem_offset_floats(a.p.T) + pipe_updater_floats(list_cap(a))) * sizeof(float);
     if (upd > smem) smem = upd;
     if (smem > (size_t)227 * 1024) return cudaErrorInvalidValue;
+    // Programmatic stream serialisation: this launch may be SCHEDULED while the previous pipelined launch of the stream
+    // is still in its update (see griddepcontrol in the kernel); after any other kind of work it starts as usual.
+    // Off for the sharded step (its completion order against the peers' launches is what tests/multi_gpu_check.py
+    // and the N = 8 timeline were measured with) and with MPPI_NO_PDL set (A/B knob).
+    static const bool no_pdl = getenv("MPPI_NO_PDL") != nullptr;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.attrs = attr; cfg.numAttrs = (no_pdl || a.peers.world > 0) ? 0 : 1;
     cudaError_t e;
 #define MPPI_LAUNCH_PIPE(PROJ, INJ)                                                    \
     do {                                                                               \
         e = ensure_smem(mppi_fused_pipe_kernel<PROJ, INJ>, smem);                      \
         if (e != cudaSuccess) return e;                                                \
-        mppi_fused_pipe_kernel<PROJ, INJ><<<grid, kPipeThreads, smem, s>>>(b);         \
+        e = cudaLaunchKernelEx(&cfg, mppi_fused_pipe_kernel<PROJ, INJ>, b);            \
+        if (e != cudaSuccess) return e;                                                \
     } while (0)
     if (proj == MPPI_PROJ_3D) {
         if (a.noise) MPPI_LAUNCH_PIPE(MPPI_PROJ_3D, true); else MPPI_LAUNCH_PIPE(MPPI_PROJ_3D, false);

@@ -1177,6 +1177,16 @@ __device__ __forceinline__ void pipe_updater(const FusedArgs& A, const MppiState
 // ------------------------------------------------------------------ the fused kernel
 // All T steps of one sample (monolithic kernel).  Steps come in (even, odd) pairs: one Philox call feeds both, and
 // the odd step skips the wheel points (dead: the slope critic reads even steps only).
+// A/B knob.  1 = fully software-pipelined rollout: noise one pair ahead AND critics one step behind (critic_step(t - 1)
+// next to chain_step(t), conditions as selects).  Bit-identical (whole GPU suite), but measured on one B200
+// (profiles/r2_ab_mono_swp.txt, r2_ab_mono_regs.txt): under the 128-register cap that four resident blocks per SM need,
+// the scheduler has no room to interleave -- C3 / C4 / C5 lose 2-3 % to the 3.6 % more instructions (selects,
+// unconditional slope terms) and K = 16384 .. 32768 gains only 1-4 %; without the cap (166 registers, three blocks per
+// SM) K = 16384 gains 19 % and K = 32768 8 %, but K >= 65536 loses 5 %.  Default 0: noise one pair ahead only (K = 16384 /
+// 32768: -3 % / -2 %, nothing lost at full occupancy; profiles/r2_ab_mono_noise_ahead.txt).
+#ifndef MPPI_MONO_SWP
+#define MPPI_MONO_SWP 0
+#endif
 template <int PROJ, bool INJECT, bool CLAMP>
 __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiState& st, const Terr& ter,
                                                const SampleConsts& sc, const NoiseKey& nk, const Smem& s, SampleAcc& a,
@@ -1185,14 +1195,72 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
     const int T = p.T;
     const UBounds ub = make_ubounds(p);
     const DumpPtrs nod = {};
-    for (int t = 0; t < T; t += 2) {
-        float e1a, e1b, e2a, e2b;
+#if MPPI_MONO_SWP
+    // One thread's step is a long DEPENDENT chain (position -> cell -> normal -> tangent -> Rodrigues) followed by
+    // critics that only read its outputs: a warp issues one instruction every ~4.6 cycles, so below four warps per
+    // scheduler the launch time is that latency, not the issue rate (K = 16384 .. 65536 per GPU: the strong-scaling
+    // end of C3, and C5).  The loop is therefore software-pipelined by hand: the iteration that runs chain_step(t)
+    // also generates the noise of the NEXT pair of steps (counter-based, depends on nothing here; the pair after the
+    // last one is computed and never used) and runs critic_step(t - 1) on the saved outputs of the previous step --
+    // independent instruction streams inside one basic block (conditions are selects, see critic_step), which the
+    // scheduler interleaves with the chain.  Every accumulator still receives its terms in the order t = 0, 1, 2, ...
+    float e1a, e1b, e2a, e2b;
+    if (INJECT) {
+        e1a = eps1[0]; e2a = eps2[0];
+        e1b = (1 < T) ? eps1[1] : 0.f;
+        e2b = (1 < T) ? eps2[1] : 0.f;
+    } else {
+        noise_pair(nk, kg, 0u, e1a, e1b, e2a, e2b);
+    }
+    StepOut se, so;                                    // outputs of the pending even / odd step
+    chain_step<PROJ, false, CLAMP, true>(p, ter, sc, a,
+                                         sample_u(s.nom1, 0, T, st.sigma1, e1a, ub.lo1, ub.hi1),
+                                         sample_u(s.nom2, 0, T, st.sigma2, e2a, ub.lo2, ub.hi2), se);
+    int t = 0;
+    for (; t + 2 < T; t += 2) {                        // steps t (pending), t + 1 and t + 2 exist
+        float n1a, n1b, n2a, n2b;
         if (INJECT) {
-            e1a = eps1[t]; e2a = eps2[t];
-            e1b = (t + 1 < T) ? eps1[t + 1] : 0.f;
-            e2b = (t + 1 < T) ? eps2[t + 1] : 0.f;
+            const int tb = min(t + 3, T - 1);
+            n1a = eps1[t + 2]; n2a = eps2[t + 2]; n1b = eps1[tb]; n2b = eps2[tb];
         } else {
-            noise_pair(nk, kg, (uint32_t)(t >> 1), e1a, e1b, e2a, e2b);
+            noise_pair(nk, kg, (uint32_t)(t >> 1) + 1u, n1a, n1b, n2a, n2b);
+        }
+        chain_step<PROJ, false, CLAMP, true>(p, ter, sc, a,
+                                             sample_u(s.nom1, t + 1, T, st.sigma1, e1b, ub.lo1, ub.hi1),
+                                             sample_u(s.nom2, t + 1, T, st.sigma2, e2b, ub.lo2, ub.hi2), so);
+        critic_step<PROJ, false, CLAMP, true, true>(p, st, ter, sc, a, t, se, 0.0f, nod, 0);
+        chain_step<PROJ, false, CLAMP, true>(p, ter, sc, a,
+                                             sample_u(s.nom1, t + 2, T, st.sigma1, n1a, ub.lo1, ub.hi1),
+                                             sample_u(s.nom2, t + 2, T, st.sigma2, n2a, ub.lo2, ub.hi2), se);
+        critic_step<PROJ, false, CLAMP, false, true>(p, st, ter, sc, a, t + 1, so, 0.0f, nod, 0);
+        e1b = n1b; e2b = n2b;
+    }
+    critic_step<PROJ, false, CLAMP, true, true>(p, st, ter, sc, a, t, se, 0.0f, nod, 0);
+    if (t + 1 < T) {
+        chain_step<PROJ, false, CLAMP, true>(p, ter, sc, a,
+                                             sample_u(s.nom1, t + 1, T, st.sigma1, e1b, ub.lo1, ub.hi1),
+                                             sample_u(s.nom2, t + 1, T, st.sigma2, e2b, ub.lo2, ub.hi2), so);
+        critic_step<PROJ, false, CLAMP, false, true>(p, st, ter, sc, a, t + 1, so, 0.0f, nod, 0);
+    }
+#else
+    // Philox + Box-Muller of the NEXT pair of steps depends on nothing in this one; generated here, unconditionally
+    // (the stream is counter-based: the pair after the last one is computed and never used), it shares a basic block
+    // with the head of the chain and fills the latency of its four corner gathers instead of preceding them.
+    float e1a, e1b, e2a, e2b;
+    if (INJECT) {
+        e1a = eps1[0]; e2a = eps2[0];
+        e1b = (1 < T) ? eps1[1] : 0.f;
+        e2b = (1 < T) ? eps2[1] : 0.f;
+    } else {
+        noise_pair(nk, kg, 0u, e1a, e1b, e2a, e2b);
+    }
+    for (int t = 0; t < T; t += 2) {
+        float n1a, n1b, n2a, n2b;
+        if (INJECT) {
+            const int ta = min(t + 2, T - 1), tb = min(t + 3, T - 1);
+            n1a = eps1[ta]; n2a = eps2[ta]; n1b = eps1[tb]; n2b = eps2[tb];
+        } else {
+            noise_pair(nk, kg, (uint32_t)(t >> 1) + 1u, n1a, n1b, n2a, n2b);
         }
         {
             const float u1 = sample_u(s.nom1, t, T, st.sigma1, e1a, ub.lo1, ub.hi1);
@@ -1204,7 +1272,9 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
             const float u2 = sample_u(s.nom2, t + 1, T, st.sigma2, e2b, ub.lo2, ub.hi2);
             sample_step<PROJ, false, CLAMP, false>(p, st, ter, sc, a, t + 1, u1, u2, nod, 0);
         }
+        e1a = n1a; e1b = n1b; e2a = n2a; e2b = n2b;
     }
+#endif
 }
 
 #ifndef MPPI_MONO_MINBLOCKS

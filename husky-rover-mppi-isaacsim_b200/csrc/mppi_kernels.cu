@@ -1177,17 +1177,17 @@ __device__ __forceinline__ void pipe_updater(const FusedArgs& A, const MppiState
 // ------------------------------------------------------------------ the fused kernel
 // All T steps of one sample (monolithic kernel).  Steps come in (even, odd) pairs: one Philox call feeds both, and
 // the odd step skips the wheel points (dead: the slope critic reads even steps only).
-// A/B knob.  1 = fully software-pipelined rollout: noise one pair ahead AND critics one step behind (critic_step(t - 1)
-// next to chain_step(t), conditions as selects).  Bit-identical (whole GPU suite), but measured on one B200
-// (profiles/r2_ab_mono_swp.txt, r2_ab_mono_regs.txt): under the 128-register cap that four resident blocks per SM need,
-// the scheduler has no room to interleave -- C3 / C4 / C5 lose 2-3 % to the 3.6 % more instructions (selects,
-// unconditional slope terms) and K = 16384 .. 32768 gains only 1-4 %; without the cap (166 registers, three blocks per
-// SM) K = 16384 gains 19 % and K = 32768 8 %, but K >= 65536 loses 5 %.  Default 0: noise one pair ahead only (K = 16384 /
-// 32768: -3 % / -2 %, nothing lost at full occupancy; profiles/r2_ab_mono_noise_ahead.txt).
-#ifndef MPPI_MONO_SWP
-#define MPPI_MONO_SWP 0
-#endif
-template <int PROJ, bool INJECT, bool CLAMP>
+// SWP = true: fully software-pipelined rollout -- noise one pair ahead AND critics one step behind (critic_step(t - 1)
+// next to chain_step(t), conditions as selects).  Bit-identical (whole GPU suite), measured on one B200
+// (profiles/r2_ab_mono_swp.txt, r2_ab_mono_regs.txt): under the 128-register cap that four resident blocks per SM need
+// the scheduler has no room to interleave (C3 / C4 / C5 lose 2-3 % to the 3.6 % more instructions; K = 16384 .. 32768
+// gain 1-4 %), but with the 166 registers it asks for K = 8192 / 16384 / 32768 gain 20 / 19 / 8 % and K >= 65536 loses
+// 5 %.  It is therefore a SECOND instantiation of the kernel (LOWOCC, own launch bounds -- the throughput instantiation's
+// code and registers are untouched), launched for single-rover grids of at most kLowOccMaxSamples samples.
+// SWP = false: noise one pair ahead only (K = 16384 / 32768: -3 % / -2 %, nothing lost at full occupancy;
+// profiles/r2_ab_mono_noise_ahead.txt).
+constexpr int kLowOccMaxSamples = 40960;
+template <int PROJ, bool INJECT, bool CLAMP, bool SWP>
 __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiState& st, const Terr& ter,
                                                const SampleConsts& sc, const NoiseKey& nk, const Smem& s, SampleAcc& a,
                                                uint32_t kg, const float* eps1, const float* eps2)
@@ -1195,7 +1195,7 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
     const int T = p.T;
     const UBounds ub = make_ubounds(p);
     const DumpPtrs nod = {};
-#if MPPI_MONO_SWP
+    if (SWP) {
     // One thread's step is a long DEPENDENT chain (position -> cell -> normal -> tangent -> Rodrigues) followed by
     // critics that only read its outputs: a warp issues one instruction every ~4.6 cycles, so below four warps per
     // scheduler the launch time is that latency, not the issue rate (K = 16384 .. 65536 per GPU: the strong-scaling
@@ -1242,7 +1242,7 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
                                              sample_u(s.nom2, t + 1, T, st.sigma2, e2b, ub.lo2, ub.hi2), so);
         critic_step<PROJ, false, CLAMP, false, true>(p, st, ter, sc, a, t + 1, so, 0.0f, nod, 0);
     }
-#else
+    } else {
     // Philox + Box-Muller of the NEXT pair of steps depends on nothing in this one; generated here, unconditionally
     // (the stream is counter-based: the pair after the last one is computed and never used), it shares a basic block
     // with the head of the chain and fills the latency of its four corner gathers instead of preceding them.
@@ -1274,7 +1274,7 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
         }
         e1a = n1a; e1b = n1b; e2a = n2a; e2b = n2b;
     }
-#endif
+    }
 }
 
 #ifndef MPPI_MONO_MINBLOCKS
@@ -1282,8 +1282,8 @@ __device__ __forceinline__ void rollout_sample(const MppiParams& p, const MppiSt
                                     // (the -DMPPI_XC build fits the same 128 registers without spilling; left alone it
                                     // takes 156 and C5 no longer fits one wave: 402 us instead of 300)
 #endif
-template <int PROJ, bool INJECT>
-__global__ void __launch_bounds__(kMaxBlock, MPPI_MONO_MINBLOCKS)
+template <int PROJ, bool INJECT, bool LOWOCC = false>
+__global__ void __launch_bounds__(kMaxBlock, LOWOCC ? 1 : MPPI_MONO_MINBLOCKS)
 mppi_fused_kernel(const __grid_constant__ FusedArgs A)
 {
     extern __shared__ float smem_raw[];
@@ -1327,9 +1327,9 @@ mppi_fused_kernel(const __grid_constant__ FusedArgs A)
         SampleAcc a;
         sample_init<PROJ>(st, ter, a);
         if (terrain_window_safe(p, st, tr))
-            rollout_sample<PROJ, INJECT, false>(p, st, ter, sc, nk, s, a, kg, eps1, eps2);
+            rollout_sample<PROJ, INJECT, false, LOWOCC>(p, st, ter, sc, nk, s, a, kg, eps1, eps2);
         else
-            rollout_sample<PROJ, INJECT, true>(p, st, ter, sc, nk, s, a, kg, eps1, eps2);
+            rollout_sample<PROJ, INJECT, true, LOWOCC>(p, st, ter, sc, nk, s, a, kg, eps1, eps2);
         cost = sample_cost(p, st, sc, a, nullptr);
         A.costs[(size_t)rover * K + k_local] = cost;
         my_oob = (unsigned)(a.oob + unit_violation(a.dev));
@@ -2065,12 +2065,21 @@ cudaError_t launch_fused(const FusedArgs& a, int proj, int n_rovers, int block, 
 {
     const dim3 grid(a.nblocks, n_rovers);
     const size_t smem = fused_smem_bytes(a.p.T, block, list_cap(a));
+    // partial occupancy (one rover, at most kLowOccMaxSamples samples): the software-pipelined instantiation
+    const bool no_lowocc = getenv("MPPI_NO_LOWOCC") != nullptr;      // A/B knob (read at every launch: tests toggle it)
+    const bool lowocc = !no_lowocc && n_rovers == 1 && (long long)a.nblocks * block <= kLowOccMaxSamples;
     cudaError_t e;
 #define MPPI_LAUNCH_FUSED(PROJ, INJ)                                              \
     do {                                                                          \
-        e = ensure_smem(mppi_fused_kernel<PROJ, INJ>, smem);                      \
-        if (e != cudaSuccess) return e;                                           \
-        mppi_fused_kernel<PROJ, INJ><<<grid, block, smem, s>>>(a);                \
+        if (lowocc) {                                                             \
+            e = ensure_smem(mppi_fused_kernel<PROJ, INJ, true>, smem);            \
+            if (e != cudaSuccess) return e;                                       \
+            mppi_fused_kernel<PROJ, INJ, true><<<grid, block, smem, s>>>(a);      \
+        } else {                                                                  \
+            e = ensure_smem(mppi_fused_kernel<PROJ, INJ, false>, smem);           \
+            if (e != cudaSuccess) return e;                                       \
+            mppi_fused_kernel<PROJ, INJ, false><<<grid, block, smem, s>>>(a);     \
+        }                                                                         \
     } while (0)
     if (proj == MPPI_PROJ_3D) {
         if (a.noise) MPPI_LAUNCH_FUSED(MPPI_PROJ_3D, true); else MPPI_LAUNCH_FUSED(MPPI_PROJ_3D, false);

@@ -400,6 +400,38 @@ def test_shared_memory_dem_tile_changes_no_bit(oracle, monkeypatch):
     assert np.array_equal(outs[0][0], ref.dump["cost"])
 
 
+@pytest.mark.parametrize("K,T", [(12288, 40), (300, 7), (4100, 31)])
+def test_low_occupancy_instantiation_changes_no_bit(oracle, monkeypatch, K, T):
+    """Single-rover launches of the monolithic kernel with at most 40960 samples run its software-pipelined
+    instantiation (critics one step behind the chain, 166 registers); MPPI_NO_LOWOCC forces the throughput instantiation.
+    Same costs, nominal, command and argmin, bit for bit -- and the costs are the oracle's (even / odd horizons, a K
+    that is no multiple of the block)."""
+    import torch
+    st = state_struct(default_state())
+    outs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("MPPI_NO_LOWOCC", "1")
+        else:
+            monkeypatch.delenv("MPPI_NO_LOWOCC", raising=False)
+        core, *_ = make_core(K, T, lambda_=30.0, variant=1)
+        core.step(st, seed=21, offset=6)
+        torch.cuda.synchronize()
+        outs.append((core.costs[0].cpu().numpy().copy(), core.optimal_u1[0].cpu().numpy().copy(),
+                     core.optimal_u2[0].cpu().numpy().copy(), core.read_stats()))
+        core.close()
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert np.array_equal(a, b)
+    assert outs[0][3]["argmin"] == outs[1][3]["argmin"] and outs[0][3]["v0"] == outs[1][3]["v0"]
+    assert outs[0][3]["w0"] == outs[1][3]["w0"]
+    dem, cm, hw = terrain("C1")
+    eps = oracle.philox_normals(21, 6, K, T)
+    z = np.zeros(T, np.float32)
+    ref = oracle.mppi_step(oracle.make_params(K=K, T=T, lam=30.0), dem, hw, cm, default_state(), z, z, eps[0], eps[1],
+                           dump=["cost"])
+    assert np.array_equal(outs[0][0], ref.dump["cost"])
+
+
 def _dem_with_hole(ahead, lateral, rows, cols):
     dem, cm, hw = terrain("C1")
     st = default_state()

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--math", default="strict")
     ap.add_argument("--rovers", type=int, default=512)
     ap.add_argument("--flush", action="store_true", help="flush L2 (256 MiB fill) before every step")
+    ap.add_argument("--K", type=int, default=0, help="override the workload's samples (single-controller workloads)")
     a = ap.parse_args()
     import torch
     from mppi_b200 import capi, synthetic as syn
@@ -44,6 +45,9 @@ def main():
     dev = torch.device("cuda", 0)
     name = "C5" if a.workload == "C5many" else a.workload
     w = syn.WORKLOADS[name]
+    if a.K:
+        import dataclasses
+        w = dataclasses.replace(w, K=a.K)
     ext = dict(cw_slope_path=50.5, cw_roll=400.0, cw_pitch=250.0) if name == "C5" else {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if a.flush else None
     if a.workload in ("C4", "C5many"):

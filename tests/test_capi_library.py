@@ -176,3 +176,20 @@ def test_ctypes_mirrors_follow_the_header_field_by_field(capi):
                 fields.append((item.lstrip("*").strip(), C.c_void_p if ptr else ctype[base]))
         mirror = [("lambda" if n == "lam" else n, t) for n, t in getattr(capi, name)._fields_]
         assert mirror == fields, name
+
+
+def test_library_holds_sm100a_code_for_every_kernel_family(capi):
+    """The shipped .so carries sm_100a SASS (no PTX-only fallback) for both fused kernels in every flavour, and BOTH
+    instantiations of the monolithic kernel (throughput and low-occupancy) -- read back with cuobjdump, no GPU needed."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-elf", capi.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out
+    for ns in ("strict", "fast", "strict_xc", "fast_xc"):
+        tag = f"N4mppi{len(ns)}{ns}"
+        assert f"{tag}22mppi_fused_pipe_kernelILi3ELb0EE" in out, ns
+        assert f"{tag}17mppi_fused_kernelILi3ELb0ELb0EE" in out, ns          # throughput instantiation
+        assert f"{tag}17mppi_fused_kernelILi3ELb0ELb1EE" in out, ns          # low-occupancy instantiation
